@@ -1,0 +1,122 @@
+"""Pin the CPU oracle to the reference's own golden vectors before trusting it.
+
+Sources of the goldens (see tests/golden/make_goldens.py):
+  tests/test_pca.py:34-59, tests/test_neighbors.py:23-48 of scverse/scanpy @ fabadb94 and the
+  in-tree fixture src/scanpy/datasets/10x_pbmc68k_reduced.zarr.zip.
+"""
+import numpy as np
+import pytest
+from scipy import sparse
+
+from oracle import fuzzy, knn, leiden, pca
+
+
+def test_pca_golden_A_pca(literals):
+    # reference: tests/test_pca.py:225-233  norm(abs(A_pca[:, :4]) - abs(X_pca)) < 2e-5 with n_comps=4
+    for arr in (literals["A_list"].astype("float32"), sparse.csr_matrix(literals["A_list"].astype("float32"))):
+        out = pca.pca_arpack(arr, 4)
+        assert np.linalg.norm(np.abs(literals["A_pca"][:, :4]) - np.abs(out["X_pca"])) < 2e-5
+    ex = pca.pca_exact_f64(literals["A_list"], 4)
+    assert np.linalg.norm(np.abs(literals["A_pca"][:, :4]) - np.abs(ex["X_pca"])) < 2e-5
+    # sign convention of the float64 restatement == sklearn's svd_flip(u_based_decision=False)
+    out64 = pca.pca_arpack(sparse.csr_matrix(literals["A_list"].astype("float64")), 4, dtype="float64")
+    np.testing.assert_allclose(ex["X_pca"], out64["X_pca"], atol=1e-9)
+    np.testing.assert_allclose(ex["variance"], out64["variance"], rtol=1e-10)
+    np.testing.assert_allclose(ex["variance_ratio"], out64["variance_ratio"], rtol=1e-10)
+
+
+def test_knn_golden_4points(literals):
+    # reference: tests/test_neighbors.py:23-39,151-192
+    x, k = literals["X4"], int(literals["n_neighbors4"])
+    idx, dist = knn.knn_brute(x, k)
+    assert (idx[:, 0] == np.arange(4)).all()
+    d = knn.sparse_from_indices_distances(idx, dist).toarray()
+    np.testing.assert_allclose(d, literals["distances_euclidean"], rtol=1e-6)
+    # constant nnz per row = k-1 and indptr = arange (src/scanpy/neighbors/_common.py:52)
+    m = knn.sparse_from_indices_distances(idx, dist)
+    assert (np.diff(m.indptr) == k - 1).all()
+
+
+def test_knn_golden_pbmc68k(pbmc68k_graph):
+    f = pbmc68k_graph
+    k = int(f["n_neighbors"][0])
+    idx, dist = knn.knn_brute(f["X_pca"][:, :30], k)
+    ok = 0
+    for i in range(700):
+        ref = set(f["dist_indices"][f["dist_indptr"][i]:f["dist_indptr"][i + 1]].tolist())
+        ok += ref == set(idx[i, 1:].tolist())
+    assert ok == 700
+    stored = np.sort(f["dist_data"].reshape(700, k - 1), axis=1)
+    np.testing.assert_allclose(dist[:, 1:], stored, rtol=1e-5)  # stored values came from an fp32 run
+
+
+def test_fuzzy_golden_4points(literals):
+    # reference: tests/test_neighbors.py:43-48,195-226 (assert_allclose default rtol=1e-7 there, fp64 umap;
+    # our restatement follows umap's float32 storage -> 1.1e-8 abs)
+    x, k = literals["X4"], int(literals["n_neighbors4"])
+    idx, dist = knn.knn_brute(x, k)
+    c, _, _ = fuzzy.fuzzy_simplicial_set(idx, dist, 4, k)
+    np.testing.assert_allclose(c.toarray(), literals["connectivities_umap"], atol=5e-8)
+    assert c.dtype == np.float32 and (c.data != 0).all()
+
+
+def _fixture_idx_dist(f):
+    n, k = 700, int(f["n_neighbors"][0])
+    di = f["dist_indices"].reshape(n, k - 1)
+    dd = f["dist_data"].reshape(n, k - 1)
+    o = np.argsort(dd, axis=1, kind="stable")  # stored CSR is column-sorted; a fresh run is distance-sorted
+    di, dd = np.take_along_axis(di, o, 1), np.take_along_axis(dd, o, 1)
+    return np.hstack([np.arange(n)[:, None], di]), np.hstack([np.zeros((n, 1)), dd]), n, k
+
+
+def test_fuzzy_golden_pbmc68k(pbmc68k_graph):
+    f = pbmc68k_graph
+    idx, dist, n, k = _fixture_idx_dist(f)
+    c, _, _ = fuzzy.fuzzy_simplicial_set(idx, dist, n, k)
+    g = sparse.csr_matrix((f["conn_data"], f["conn_indices"], f["conn_indptr"]), shape=(n, n))
+    assert c.nnz == g.nnz == 9992
+    c.sort_indices(); g.sort_indices()
+    assert (c.indices == g.indices).all() and (c.indptr == g.indptr).all()
+    np.testing.assert_allclose(c.data, g.data, atol=5e-7)
+    assert abs(c - c.T).max() == 0
+
+
+def test_leiden_oracle_properties(pbmc68k_graph):
+    # properties the reference pins (tests/test_clustering.py:67-102, tests/test_metrics.py:311-344)
+    import networkx as nx
+
+    f = pbmc68k_graph
+    n = 700
+    g = sparse.csr_matrix((f["conn_data"], f["conn_indices"], f["conn_indptr"]), shape=(n, n))
+    m0, q0, _ = leiden.leiden(g, seed=0)
+    m0b, q0b, _ = leiden.leiden(g, seed=0)
+    assert (m0 == m0b).all() and q0 == q0b  # same seed -> identical
+    assert 0.0 <= q0 <= 1.0
+    sizes = np.bincount(m0)
+    assert (np.diff(sizes) <= 0).all()  # renumbered by decreasing size ('0' = largest)
+    assert abs(leiden.modularity(g, m0) - q0) < 1e-12
+    gx = nx.from_scipy_sparse_array(g)
+    comms = [set(np.flatnonzero(m0 == c).tolist()) for c in range(m0.max() + 1)]
+    assert abs(nx.community.modularity(gx, comms, weight="weight") - q0) < 1e-10
+    # independent quality floor: at least as good as networkx's (native) Louvain
+    lc = nx.community.louvain_communities(gx, weight="weight", seed=0)
+    assert q0 >= nx.community.modularity(gx, lc, weight="weight") - 1e-3
+    # resolution changes the number of communities monotonically-ish
+    m_lo, _, _ = leiden.leiden(g, resolution=0.2, seed=0)
+    m_hi, _, _ = leiden.leiden(g, resolution=3.0, seed=0)
+    assert m_lo.max() < m0.max() < m_hi.max()
+
+
+def test_leiden_oracle_planted():
+    from sklearn.metrics import adjusted_rand_score
+
+    rs = np.random.RandomState(0)
+    nb, sz = 12, 60
+    n = nb * sz
+    lab = np.repeat(np.arange(nb), sz)
+    p = np.where(lab[:, None] == lab[None, :], 0.3, 0.002)
+    a = np.triu(rs.rand(n, n) < p, 1).astype(np.float64)
+    a = a + a.T
+    m, q, _ = leiden.leiden(sparse.csr_matrix(a), seed=3)
+    assert adjusted_rand_score(lab, m) == pytest.approx(1.0)
+    assert q > 0.8
