@@ -1,0 +1,158 @@
+/* scanpy_b200.h — C ABI of libscanpy_b200.so: the B200-native (sm_100a) kernels behind
+ * scanpy's  sc.pp.pca -> sc.pp.neighbors -> sc.tl.leiden  hot path.
+ *
+ * The reference (scverse/scanpy @ fabadb94) is pure Python and has no FFI of its own: its hot
+ * path is three call sites into third-party native code.  Each entry point below replaces one of
+ * those call sites and is what a reference-side binding (ctypes) would bind:
+ *
+ *   sb2_pca_csr_f32            <- sklearn PCA(svd_solver='arpack').fit_transform(csr)
+ *                                 src/scanpy/preprocessing/_pca/__init__.py:282-291,308
+ *                                 (solver 1: the covariance_eigh route, _pca/_dask.py:143-213 +
+ *                                  _pca/_kernels.py:14-58)
+ *   sb2_knn_l2_f32             <- KNeighborsTransformer(algorithm='brute').fit_transform(x)
+ *                                 src/scanpy/neighbors/__init__.py:754-768,638
+ *   sb2_fuzzy_simplicial_set_f32 <- umap.umap_.fuzzy_simplicial_set(...).tocsr()
+ *                                 src/scanpy/neighbors/_connectivity.py:124-138
+ *   sb2_leiden_csr_f32         <- leidenalg.find_partition / Graph.community_leiden
+ *                                 src/scanpy/tools/_leiden.py:184-187,195-196 (graph build
+ *                                 src/scanpy/_utils/__init__.py:278-306 is eliminated: CSR in)
+ *
+ * Conventions
+ *   - every function returns int32: 0 ok, <0 error (SB2_E_*); sb2_last_error() gives the text
+ *     (thread-local, library-owned, valid until the next failing call on that thread).
+ *   - pointers prefixed d_ are DEVICE pointers into memory the caller owns (the Python host
+ *     allocates them as torch CUDA tensors); h_ are HOST pointers.  No torch types cross the ABI.
+ *   - work is enqueued on the ctx's CUDA stream.  Functions that return host-visible scalars
+ *     (nnz, counters, modularity) synchronise that stream before returning; the others are async.
+ *   - a ctx is bound to one device and is not thread-safe.  No callbacks, no exceptions.
+ *   - indptr is int64 (10M x 4k at 5 % has > 2^31 non-zeros), column / neighbour indices int32.
+ */
+#ifndef SCANPY_B200_H
+#define SCANPY_B200_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SB2_OK 0
+#define SB2_E_BADARG (-1)
+#define SB2_E_CUDA (-2)
+#define SB2_E_NCCL (-3)
+#define SB2_E_OOM (-4)
+#define SB2_E_NOTCONV (-5)
+#define SB2_E_UNSUPPORTED (-6)
+
+typedef struct sb2_ctx sb2_ctx;
+
+typedef struct sb2_device_info {
+  int32_t device;
+  int32_t sm_count;
+  int32_t cc_major, cc_minor;
+  int32_t clock_khz;        /* max SM clock */
+  int32_t mem_clock_khz;
+  int32_t l2_bytes;
+  int32_t smem_per_block_optin;
+  int64_t total_mem;
+  char name[64];
+} sb2_device_info;
+
+/* per-call statistics (all optional: pass NULL) */
+typedef struct sb2_pca_info {
+  int32_t iterations;       /* operator applications */
+  int32_t converged;        /* 1 if residual test met */
+  double max_rel_residual;  /* max_j ||A v_j - theta_j v_j|| / theta_1 over the k kept pairs */
+  double total_var;         /* sum of per-gene variances (ddof=1) */
+} sb2_pca_info;
+
+typedef struct sb2_knn_info {
+  int64_t n_uncertified;    /* query rows that needed the exact fallback */
+  float max_norm;
+} sb2_knn_info;
+
+typedef struct sb2_leiden_info {
+  int32_t passes;           /* whole Leiden iterations run */
+  int32_t levels;           /* aggregation levels of the last pass */
+  int64_t moves;            /* accepted local moves, all levels */
+} sb2_leiden_info;
+
+int32_t sb2_version(void);
+const char* sb2_last_error(void);
+
+/* stream: the cudaStream_t (as void*) to enqueue on; NULL means the legacy default stream unless
+ * flags has SB2_CTX_PRIVATE_STREAM, in which case the ctx creates its own non-blocking stream. */
+#define SB2_CTX_PRIVATE_STREAM 1u
+int32_t sb2_ctx_create(int32_t device, void* stream, uint32_t flags, sb2_ctx** out);
+int32_t sb2_ctx_destroy(sb2_ctx* ctx);
+int32_t sb2_ctx_sync(sb2_ctx* ctx);
+int32_t sb2_device_info_get(sb2_ctx* ctx, sb2_device_info* out);
+/* number of kernel launches this ctx has enqueued so far (bench.py's gpu_launches) */
+int64_t sb2_ctx_launch_count(sb2_ctx* ctx);
+
+/* Multi-GPU (one process per GPU): rank 0 calls sb2_comm_unique_id, the 128 bytes travel to the
+ * other ranks through the host's own rendezvous (torch.distributed broadcast), every rank calls
+ * sb2_comm_init.  With a communicator attached, sb2_pca_csr_f32 treats its CSR as the rank's row
+ * shard and all-reduces its small dense reductions. */
+int32_t sb2_comm_unique_id(void* h_id128);
+int32_t sb2_comm_init(sb2_ctx* ctx, int32_t n_ranks, int32_t rank, const void* h_id128);
+int32_t sb2_comm_allgather(sb2_ctx* ctx, const void* d_send, void* d_recv, int64_t bytes_per_rank);
+int32_t sb2_comm_allreduce_f64(sb2_ctx* ctx, double* d_buf, int64_t count);
+
+/* ---- PCA: top-k principal components of the implicitly centred CSR matrix (A1 in SURVEY.md) ----
+ * solver 0: block subspace iteration driven by CSR x dense SpMM passes (replaces ARPACK).
+ * solver 1: exact Gram route  G = X^T X (one CSR pass) -> covariance -> dense block iteration.
+ * n_total = number of rows over ALL ranks (== n when no communicator is attached).
+ * Outputs: d_x_pca [n x k] float32 row-major, d_components [k x g] float32 (rows = PCs, sign fixed by
+ * svd_flip(u_based_decision=False)), h_var[k], h_var_ratio[k], h_mean[g] (host, float64). */
+int32_t sb2_pca_csr_f32(sb2_ctx* ctx, int64_t n, int64_t n_total, int32_t g, const int64_t* d_indptr,
+                        const int32_t* d_indices, const float* d_data, int32_t k, int32_t solver,
+                        int32_t max_iter, double tol, uint64_t seed, float* d_x_pca, float* d_components,
+                        double* h_var, double* h_var_ratio, double* h_mean, sb2_pca_info* info);
+
+/* building blocks of the above, exported for tests / profiling */
+int32_t sb2_csr_col_stats(sb2_ctx* ctx, int64_t n, int32_t g, const int64_t* d_indptr, const int32_t* d_indices,
+                          const float* d_data, double* d_col_sum, double* d_col_sumsq);
+/* Y[n x l] = X * B[g x l] - 1 * shift[l]  (shift may be NULL) */
+int32_t sb2_spmm_csr(sb2_ctx* ctx, int64_t n, int32_t g, int32_t l, const int64_t* d_indptr,
+                     const int32_t* d_indices, const float* d_data, const float* d_b, const float* d_shift,
+                     float* d_y);
+/* Z[g x l] (float64) = X^T * Y[n x l] */
+int32_t sb2_spmm_csr_t(sb2_ctx* ctx, int64_t n, int32_t g, int32_t l, const int64_t* d_indptr,
+                       const int32_t* d_indices, const float* d_data, const float* d_y, double* d_z);
+/* G[g x g] (float64, full symmetric) = X^T X */
+int32_t sb2_csr_gram(sb2_ctx* ctx, int64_t n, int32_t g, const int64_t* d_indptr, const int32_t* d_indices,
+                     const float* d_data, double* d_gram);
+
+/* ---- exact brute-force kNN (euclidean) -----------------------------------------------------
+ * points: d_x [n_points x d] float32 row-major.  Queries are rows [q0, q0+n_query) of the same
+ * array (q0 % 128 == 0 unless n_query == n_points).  k includes the query itself: column 0 of
+ * the outputs is the query row with distance 0 (src/scanpy/neighbors/_common.py:74-98).
+ * Outputs [n_query x k]: d_idx int32 (global row ids), d_dist float64, ascending by (distance, id).
+ * Exactness: a fast fp32 pass proposes 32 candidates per query, an fp64 re-score certifies the
+ * top-k against a rounding-error bound, uncertified rows are recomputed exactly. */
+int32_t sb2_knn_l2_f32(sb2_ctx* ctx, int64_t n_points, int32_t d, const float* d_x, int64_t q0, int64_t n_query,
+                       int32_t k, int32_t* d_idx, double* d_dist, sb2_knn_info* info);
+
+/* ---- UMAP fuzzy simplicial set -> symmetric connectivities CSR -------------------------------
+ * d_knn_idx/d_knn_dist [n x k] (column 0 = self), as produced by sb2_knn_l2_f32.
+ * Output CSR: d_indptr int64[n+1], d_indices int32[cap], d_data float32[cap]; cap >= 2*n*(k-1) is
+ * always enough.  Rows sorted by column, no explicit zeros, zero diagonal. */
+int32_t sb2_fuzzy_simplicial_set_f32(sb2_ctx* ctx, int64_t n, int32_t k, const int32_t* d_knn_idx,
+                                     const double* d_knn_dist, float set_op_mix_ratio, float local_connectivity,
+                                     int64_t* d_indptr, int32_t* d_indices, float* d_data, int64_t cap,
+                                     int64_t* h_nnz, float* d_sigmas, float* d_rhos);
+
+/* ---- Leiden on a symmetric weighted CSR graph ------------------------------------------------
+ * n_iterations < 0: iterate until a whole pass moves nothing.  Output membership int32[n]
+ * renumbered by decreasing community size; *h_modularity at the given resolution. */
+int32_t sb2_leiden_csr_f32(sb2_ctx* ctx, int64_t n, const int64_t* d_indptr, const int32_t* d_indices,
+                           const float* d_weights, double resolution, int32_t n_iterations, uint64_t seed,
+                           int32_t* d_membership, double* h_modularity, int32_t* h_n_comms, sb2_leiden_info* info);
+int32_t sb2_modularity_csr_f32(sb2_ctx* ctx, int64_t n, const int64_t* d_indptr, const int32_t* d_indices,
+                               const float* d_weights, double resolution, const int32_t* d_membership,
+                               double* h_modularity);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SCANPY_B200_H */

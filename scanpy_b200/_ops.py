@@ -1,0 +1,160 @@
+"""Host-side drivers of the C-ABI kernels: numpy/scipy in, numpy/scipy out.
+
+Each function stages its inputs in (pinned) host memory, copies them to the device with torch,
+calls ONE C-ABI entry point of libscanpy_b200.so (include/scanpy_b200.h) and copies the results
+back.  torch is plumbing only (allocation, copies, stream); there is no CPU code path.
+`*_device` variants take/return torch CUDA tensors so a pipeline can keep intermediates in HBM.
+"""
+from __future__ import annotations
+
+from ctypes import byref, c_double, c_int32, c_int64
+
+import numpy as np
+
+from . import _abi
+from ._abi import KnnInfo, LeidenInfo, PcaInfo, check, ptr
+
+
+def _torch():
+    import torch
+
+    return torch
+
+
+def _to_device(arr: np.ndarray, *, pin: bool = True):
+    """numpy -> CUDA tensor through a pinned staging buffer (async H2D on the current stream)."""
+    torch = _torch()
+    t = torch.from_numpy(np.ascontiguousarray(arr))
+    if pin and t.numel() > 0:
+        try:
+            t = t.pin_memory()
+        except RuntimeError:
+            pass
+    return t.to("cuda", non_blocking=True)
+
+
+def csr_to_device(x):
+    """scipy CSR (float32/float64 data, any index width) -> (indptr int64, indices int32, data float32) CUDA tensors."""
+    indptr = np.asarray(x.indptr, dtype=np.int64)
+    indices = np.asarray(x.indices, dtype=np.int32)
+    data = np.asarray(x.data, dtype=np.float32)
+    return _to_device(indptr), _to_device(indices), _to_device(data)
+
+
+# ------------------------------------------------------------------------------------------ PCA
+def pca_csr_device(ctx, d_indptr, d_indices, d_data, n: int, g: int, n_comps: int, *, solver: int = 0,
+                   max_iter: int = 0, tol: float = 0.0, seed: int = 0, n_total: int | None = None):
+    torch = _torch()
+    x_pca = torch.empty((n, n_comps), dtype=torch.float32, device="cuda")
+    comps = torch.empty((n_comps, g), dtype=torch.float32, device="cuda")
+    var = np.empty(n_comps, np.float64)
+    ratio = np.empty(n_comps, np.float64)
+    mean = np.empty(g, np.float64)
+    info = PcaInfo()
+    check(ctx.lib.sb2_pca_csr_f32(ctx.handle, n, n if n_total is None else n_total, g, ptr(d_indptr), ptr(d_indices),
+                                  ptr(d_data), n_comps, solver, max_iter, tol, seed, ptr(x_pca), ptr(comps),
+                                  ptr(var), ptr(ratio), ptr(mean), byref(info)))
+    return dict(X_pca=x_pca, components=comps, variance=var, variance_ratio=ratio, mean=mean,
+                iterations=info.iterations, converged=bool(info.converged), max_rel_residual=info.max_rel_residual,
+                total_var=info.total_var)
+
+
+def pca_csr(x, n_comps: int, *, solver: int = 0, max_iter: int = 0, tol: float = 0.0, seed: int = 0, ctx=None):
+    """Top-n_comps PCA of a scipy CSR matrix; host arrays out (X_pca float32 [n,k], components float32 [k,g])."""
+    ctx = ctx or _abi.default_context()
+    n, g = x.shape
+    d_indptr, d_indices, d_data = csr_to_device(x)
+    out = pca_csr_device(ctx, d_indptr, d_indices, d_data, n, g, n_comps, solver=solver, max_iter=max_iter, tol=tol,
+                         seed=seed)
+    out["X_pca"] = out["X_pca"].cpu().numpy()
+    out["components"] = out["components"].cpu().numpy()
+    return out
+
+
+# ------------------------------------------------------------------------------------------ kNN
+def knn_device(ctx, d_x, n_neighbors: int, *, q0: int = 0, n_query: int | None = None):
+    torch = _torch()
+    n, d = d_x.shape
+    n_query = n - q0 if n_query is None else n_query
+    idx = torch.empty((n_query, n_neighbors), dtype=torch.int32, device="cuda")
+    dist = torch.empty((n_query, n_neighbors), dtype=torch.float64, device="cuda")
+    info = KnnInfo()
+    check(ctx.lib.sb2_knn_l2_f32(ctx.handle, n, d, ptr(d_x), q0, n_query, n_neighbors, ptr(idx), ptr(dist),
+                                 byref(info)))
+    return idx, dist, dict(n_uncertified=int(info.n_uncertified), max_norm=float(info.max_norm))
+
+
+def knn(x: np.ndarray, n_neighbors: int, *, ctx=None):
+    """Exact euclidean kNN incl. self in column 0 -> (indices int32 [n,k], distances float64 [n,k], info)."""
+    ctx = ctx or _abi.default_context()
+    d_x = _to_device(np.asarray(x, dtype=np.float32))
+    idx, dist, info = knn_device(ctx, d_x, n_neighbors)
+    return idx.cpu().numpy(), dist.cpu().numpy(), info
+
+
+# ------------------------------------------------------------------------------------------ graph
+def fuzzy_simplicial_set_device(ctx, d_idx, d_dist, n: int, k: int, *, set_op_mix_ratio: float = 1.0,
+                                local_connectivity: float = 1.0):
+    torch = _torch()
+    cap = 2 * n * max(k - 1, 1)
+    indptr = torch.empty(n + 1, dtype=torch.int64, device="cuda")
+    indices = torch.empty(cap, dtype=torch.int32, device="cuda")
+    data = torch.empty(cap, dtype=torch.float32, device="cuda")
+    sig = torch.empty(n, dtype=torch.float32, device="cuda")
+    rho = torch.empty(n, dtype=torch.float32, device="cuda")
+    nnz = c_int64()
+    check(ctx.lib.sb2_fuzzy_simplicial_set_f32(ctx.handle, n, k, ptr(d_idx), ptr(d_dist), set_op_mix_ratio,
+                                               local_connectivity, ptr(indptr), ptr(indices), ptr(data), cap,
+                                               byref(nnz), ptr(sig), ptr(rho)))
+    m = nnz.value
+    return indptr, indices[:m], data[:m], sig, rho
+
+
+def fuzzy_simplicial_set(knn_indices: np.ndarray, knn_dists: np.ndarray, *, ctx=None, **kw):
+    """-> scipy CSR float32 connectivities (symmetric, sorted indices, no explicit zeros)."""
+    from scipy import sparse
+
+    ctx = ctx or _abi.default_context()
+    n, k = knn_indices.shape
+    d_idx = _to_device(np.asarray(knn_indices, dtype=np.int32))
+    d_dist = _to_device(np.asarray(knn_dists, dtype=np.float64))
+    indptr, indices, data, sig, rho = fuzzy_simplicial_set_device(ctx, d_idx, d_dist, n, k, **kw)
+    ip = indptr.cpu().numpy()
+    c = sparse.csr_matrix((data.cpu().numpy(), indices.cpu().numpy(), ip if ip[-1] >= 2**31 else ip.astype(np.int32)),
+                          shape=(n, n))
+    return c, sig.cpu().numpy(), rho.cpu().numpy()
+
+
+def leiden_device(ctx, d_indptr, d_indices, d_weights, n: int, *, resolution: float = 1.0, n_iterations: int = -1,
+                  seed: int = 0):
+    torch = _torch()
+    member = torch.empty(n, dtype=torch.int32, device="cuda")
+    q = c_double()
+    nc = c_int32()
+    info = LeidenInfo()
+    check(ctx.lib.sb2_leiden_csr_f32(ctx.handle, n, ptr(d_indptr), ptr(d_indices), ptr(d_weights), float(resolution),
+                                     int(n_iterations), int(seed), ptr(member), byref(q), byref(nc), byref(info)))
+    return member, q.value, nc.value, dict(passes=info.passes, levels=info.levels, moves=int(info.moves))
+
+
+def leiden(adj, *, resolution: float = 1.0, n_iterations: int = -1, seed: int = 0, ctx=None):
+    """Leiden on a symmetric scipy CSR adjacency -> (membership int32 [n], modularity, info)."""
+    ctx = ctx or _abi.default_context()
+    adj = adj.tocsr()
+    n = adj.shape[0]
+    d_indptr, d_indices, d_w = csr_to_device(adj)
+    member, q, nc, info = leiden_device(ctx, d_indptr, d_indices, d_w, n, resolution=resolution,
+                                        n_iterations=n_iterations, seed=seed)
+    info["n_communities"] = nc
+    return member.cpu().numpy(), q, info
+
+
+def modularity(adj, membership, *, resolution: float = 1.0, ctx=None) -> float:
+    ctx = ctx or _abi.default_context()
+    adj = adj.tocsr()
+    d_indptr, d_indices, d_w = csr_to_device(adj)
+    d_m = _to_device(np.asarray(membership, dtype=np.int32))
+    q = c_double()
+    check(ctx.lib.sb2_modularity_csr_f32(ctx.handle, adj.shape[0], ptr(d_indptr), ptr(d_indices), ptr(d_w),
+                                         float(resolution), ptr(d_m), byref(q)))
+    return q.value

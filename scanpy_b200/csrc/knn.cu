@@ -1,0 +1,461 @@
+// knn.cu — exact brute-force euclidean kNN on the n x d float32 embedding (sm_100a).
+//
+// Replaces sklearn's KNeighborsTransformer(algorithm='brute') as built by the reference at
+// src/scanpy/neighbors/__init__.py:754-768 (ArgKmin: GEMM-shaped middle term with fp64
+// accumulation + per-row heaps).  Pipeline:
+//
+//   knn_prep_kernel     X[n,d] row-major  ->  Xt: tiles of 128 points, k-major [d+1][128]; the extra
+//                       row holds hn_j = -|x_j|^2/2, so one 1-D bulk (TMA) copy stages a whole tile.
+//   knn_pass1_kernel    CTA = 128 queries, sweeps all candidate tiles through a 3-stage
+//                       cp.async.bulk + mbarrier ring.  8 compute warps, each owns 16 query rows
+//                       exclusively; a lane's register micro-tile is 16 queries x 4 candidates
+//                       (64 FFMA per k-step).  score = q.c - |c|^2/2 (larger = closer; d^2 = |q|^2 - 2 score)
+//                       lands in the accumulators with no epilogue arithmetic (accumulators start
+//                       at hn).  Per query row the warp keeps the best 32 scores as a sorted list
+//                       distributed over its lanes (one entry per lane, in registers); a candidate
+//                       is examined only if it beats the row's current 32nd best (one FSETP per
+//                       element + one ballot per row and tile; insertions are O(32 ln n) per row).
+//   knn_rescore_kernel  warp per query: exact fp64 |q-c|^2 of the 32 proposals, warp bitonic sort by
+//                       (d^2, id), self forced to column 0, top-k out.  Certificate: every point
+//                       not proposed has fp32 score <= s32, hence true d^2 >= |q|^2 - 2 (s32 + eps);
+//                       if the exact k-th d^2 is below that bound the row is provably exact.
+//   knn_fallback_kernel rows without a certificate (ties, duplicates, pathological scales) are
+//                       recomputed exactly in fp64 against all points.
+#include <float.h>
+#include <string.h>
+
+#include "common.cuh"
+
+namespace {
+
+constexpr int TILE = 128;      // points per tile (queries per CTA, candidates per stage)
+constexpr int LISTM = 32;      // proposals kept per query (one per lane)
+constexpr int NWARP_C = 8;     // compute warps
+constexpr int PASS1_THREADS = (NWARP_C + 1) * 32;
+
+// ------------------------------------------------------------------------------------------------
+__global__ void knn_prep_kernel(const float* __restrict__ X, int64_t n, int d, float* __restrict__ Xt,
+                                unsigned int* __restrict__ maxnorm_bits) {
+  extern __shared__ float s[];  // [128][d] staged chunk
+  const int64_t t = blockIdx.x;
+  const int64_t p0 = t * TILE;
+  const int rows = (n - p0 < TILE) ? (int)(n - p0) : TILE;
+  const float* src = X + p0 * d;
+  for (int i = threadIdx.x; i < TILE * d; i += blockDim.x) s[i] = (i < rows * d) ? src[i] : 0.0f;
+  __syncthreads();
+  float* dst = Xt + t * (int64_t)(d + 1) * TILE;
+  for (int i = threadIdx.x; i < TILE * d; i += blockDim.x) {
+    int k = i / TILE, j = i % TILE;
+    dst[i] = s[j * d + k];
+  }
+  if (threadIdx.x < TILE) {
+    int j = threadIdx.x;
+    double acc = 0.0;
+    for (int k = 0; k < d; ++k) {
+      double v = s[j * d + k];
+      acc += v * v;
+    }
+    float hn = (j < rows) ? (float)(-0.5 * acc) : -INFINITY;
+    dst[d * TILE + j] = hn;
+    if (j < rows) atomicMax(maxnorm_bits, __float_as_uint((float)acc * (1.0f + 1e-6f)));
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE_%=;\n"
+      "bra WAIT_%=;\n"
+      "DONE_%=:\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+// 1-D bulk async copy global -> shared (TMA engine, SASS UBLKCP), completion on an mbarrier
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+
+template <int NST>
+__global__ void __launch_bounds__(PASS1_THREADS, 1)
+knn_pass1_kernel(const float* __restrict__ Xt, int d, int64_t n_tiles, int64_t qtile0, int64_t n_query,
+                 float* __restrict__ cand_score, int32_t* __restrict__ cand_idx) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  const int chunk_f = (d + 1) * TILE;              // floats per tile chunk
+  const uint32_t chunk_b = (uint32_t)chunk_f * 4u;  // bytes (multiple of 512)
+  float* As = reinterpret_cast<float*>(smem_raw);
+  float* Bs0 = As + chunk_f;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(Bs0 + (size_t)NST * chunk_f);
+  uint64_t* full = bars;            // [NST]
+  uint64_t* empty = bars + NST;     // [NST]
+  uint64_t* afull = bars + 2 * NST;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < NST; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], NWARP_C);
+    }
+    mbar_init(afull, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+
+  const int64_t qt = qtile0 + blockIdx.x;
+  if (warp == NWARP_C) {
+    // ---------------- producer warp: one elected lane drives the bulk-copy ring ----------------
+    if (lane == 0) {
+      mbar_expect_tx(afull, chunk_b);
+      bulk_g2s(As, Xt + qt * chunk_f, chunk_b, afull);
+      for (int64_t c = 0; c < n_tiles; ++c) {
+        const int s = (int)(c % NST);
+        const int64_t use = c / NST;
+        if (use > 0) mbar_wait(&empty[s], (uint32_t)((use - 1) & 1));
+        mbar_expect_tx(&full[s], chunk_b);
+        bulk_g2s(Bs0 + (size_t)s * chunk_f, Xt + c * chunk_f, chunk_b, &full[s]);
+      }
+    }
+    return;
+  }
+
+  // ---------------- compute warps ----------------
+  float lv[16];
+  int32_t li[16];
+  float th[16];
+#pragma unroll
+  for (int r = 0; r < 16; ++r) {
+    lv[r] = -INFINITY;
+    li[r] = -1;
+    th[r] = -INFINITY;
+  }
+  mbar_wait(afull, 0);
+  const float* Aw = As + 16 * warp;
+
+  for (int64_t c = 0; c < n_tiles; ++c) {
+    const int s = (int)(c % NST);
+    mbar_wait(&full[s], (uint32_t)((c / NST) & 1));
+    const float* Bs = Bs0 + (size_t)s * chunk_f + 4 * lane;
+
+    float acc[16][4];
+    {
+      const float4 h = *reinterpret_cast<const float4*>(Bs + d * TILE);
+#pragma unroll
+      for (int r = 0; r < 16; ++r) {
+        acc[r][0] = h.x; acc[r][1] = h.y; acc[r][2] = h.z; acc[r][3] = h.w;
+      }
+    }
+#pragma unroll 2
+    for (int k = 0; k < d; ++k) {
+      const float4 b = *reinterpret_cast<const float4*>(Bs + k * TILE);
+      const float4 a0 = *reinterpret_cast<const float4*>(Aw + k * TILE);
+      const float4 a1 = *reinterpret_cast<const float4*>(Aw + k * TILE + 4);
+      const float4 a2 = *reinterpret_cast<const float4*>(Aw + k * TILE + 8);
+      const float4 a3 = *reinterpret_cast<const float4*>(Aw + k * TILE + 12);
+      const float a[16] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w,
+                           a2.x, a2.y, a2.z, a2.w, a3.x, a3.y, a3.z, a3.w};
+#pragma unroll
+      for (int r = 0; r < 16; ++r) {
+        acc[r][0] = fmaf(a[r], b.x, acc[r][0]);
+        acc[r][1] = fmaf(a[r], b.y, acc[r][1]);
+        acc[r][2] = fmaf(a[r], b.z, acc[r][2]);
+        acc[r][3] = fmaf(a[r], b.w, acc[r][3]);
+      }
+    }
+    // release the stage as early as possible (all smem reads of this stage are done)
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&empty[s]);
+
+    const int32_t base = (int32_t)(c * TILE);
+#pragma unroll
+    for (int r = 0; r < 16; ++r) {
+      const bool any = (acc[r][0] > th[r]) | (acc[r][1] > th[r]) | (acc[r][2] > th[r]) | (acc[r][3] > th[r]);
+      if (__ballot_sync(0xffffffffu, any)) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          unsigned mj = __ballot_sync(0xffffffffu, acc[r][j] > th[r]);
+          while (mj) {
+            const int src = __ffs(mj) - 1;
+            mj &= mj - 1;
+            const float v = __shfl_sync(0xffffffffu, acc[r][j], src);
+            if (v > th[r]) {  // warp-uniform: th may have risen since the ballot
+              const int32_t id = base + 4 * src + j;
+              const int pos = __popc(__ballot_sync(0xffffffffu, lv[r] >= v));
+              const float up_v = __shfl_up_sync(0xffffffffu, lv[r], 1);
+              const int32_t up_i = __shfl_up_sync(0xffffffffu, li[r], 1);
+              if (lane > pos) { lv[r] = up_v; li[r] = up_i; }
+              else if (lane == pos) { lv[r] = v; li[r] = id; }
+              th[r] = __shfl_sync(0xffffffffu, lv[r], 31);
+            }
+          }
+        }
+      }
+    }
+  }
+
+  // proposals out: row-major [n_query][32], lane = rank (0 = best)
+#pragma unroll
+  for (int r = 0; r < 16; ++r) {
+    const int64_t q = (int64_t)blockIdx.x * TILE + 16 * warp + r;
+    if (q < n_query) {
+      cand_score[q * LISTM + lane] = lv[r];
+      cand_idx[q * LISTM + lane] = li[r];
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ bool lex_less(double ka, int ia, double kb, int ib) {
+  return ka < kb || (ka == kb && ia < ib);
+}
+
+__global__ void knn_rescore_kernel(const float* __restrict__ X, int64_t n_points, int d, int64_t q0, int64_t n_query,
+                                   int k, const float* __restrict__ cand_score, const int32_t* __restrict__ cand_idx,
+                                   const unsigned int* __restrict__ maxnorm_bits, int32_t* __restrict__ idx_out,
+                                   double* __restrict__ dist_out, int32_t* __restrict__ work_q,
+                                   double* __restrict__ work_ub, unsigned long long* __restrict__ work_cnt) {
+  const int lane = threadIdx.x & 31;
+  const int64_t ql = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (ql >= n_query) return;
+  const int64_t q = q0 + ql;
+  const float* xq = X + q * d;
+  const int32_t ci = cand_idx[ql * LISTM + lane];
+  const float cs = cand_score[ql * LISTM + lane];
+  double key = DBL_MAX;
+  double qn = 0.0;
+  {
+    const float* xc = X + (int64_t)(ci < 0 ? 0 : ci) * d;
+    double acc = 0.0;
+    for (int j = 0; j < d; ++j) {
+      const double a = xq[j];
+      const double df = a - (double)xc[j];
+      acc = fma(df, df, acc);
+      qn = fma(a, a, qn);
+    }
+    if (ci >= 0) key = (ci == q) ? -1.0 : acc;
+  }
+  int32_t id = ci < 0 ? INT32_MAX : ci;
+  // warp bitonic sort ascending by (key, id)
+#pragma unroll
+  for (int kk = 2; kk <= 32; kk <<= 1) {
+#pragma unroll
+    for (int j = kk >> 1; j > 0; j >>= 1) {
+      const double ok = __shfl_xor_sync(0xffffffffu, key, j);
+      const int32_t oi = __shfl_xor_sync(0xffffffffu, id, j);
+      const bool want_min = ((lane & j) == 0) == ((lane & kk) == 0);
+      const bool other_less = lex_less(ok, oi, key, id);
+      const bool take = want_min ? other_less : lex_less(key, id, ok, oi);
+      if (take) { key = ok; id = oi; }
+    }
+  }
+  // the query itself must sit in column 0 (src/scanpy/neighbors/_common.py:74-98); if it was not
+  // proposed at all (> 32 exact duplicates with smaller scores cannot happen: its own score is the
+  // row maximum up to rounding, but a flood of duplicates can push it out) the row is not certified.
+  const bool self_first = __shfl_sync(0xffffffffu, id, 0) == (int32_t)q;
+  const double kth = __shfl_sync(0xffffffffu, key, k - 1);
+  const float s32 = __shfl_sync(0xffffffffu, cs, 31);  // proposals are stored best..worst
+  const int32_t i32 = __shfl_sync(0xffffffffu, ci, 31);
+  bool certified;
+  if (i32 < 0) {
+    certified = true;  // fewer than 32 points exist: the proposal list is the whole data set
+  } else {
+    const double R = sqrt((double)__uint_as_float(*maxnorm_bits));
+    const double eps = 1.5 * (double)(d + 2) * 5.9604644775390625e-08 * (0.5 * R * R + sqrt(qn) * R);
+    const double bound = qn - 2.0 * ((double)s32 + eps);
+    certified = self_first && (kth < bound);
+  }
+  if (lane < k) {
+    idx_out[ql * k + lane] = id;
+    dist_out[ql * k + lane] = key < 0.0 ? 0.0 : sqrt(key);
+  }
+  if (!certified && lane == 0) {
+    const unsigned long long w = atomicAdd(work_cnt, 1ull);
+    work_q[w] = (int32_t)ql;
+    work_ub[w] = self_first ? kth : DBL_MAX;
+  }
+}
+
+// exact fallback: one CTA per uncertified query, fp64 distances to every point
+constexpr int FB_THREADS = 256;
+constexpr int FB_BUF = 2048;
+
+__device__ void block_bitonic_sort(double* keys, int32_t* ids, int n_pow2) {
+  for (int kk = 2; kk <= n_pow2; kk <<= 1) {
+    for (int j = kk >> 1; j > 0; j >>= 1) {
+      for (int i = threadIdx.x; i < n_pow2; i += blockDim.x) {
+        const int ixj = i ^ j;
+        if (ixj > i) {
+          const bool asc = (i & kk) == 0;
+          const bool gt = lex_less(keys[ixj], ids[ixj], keys[i], ids[i]);
+          if (gt == asc) {
+            double tk = keys[i]; keys[i] = keys[ixj]; keys[ixj] = tk;
+            int32_t ti = ids[i]; ids[i] = ids[ixj]; ids[ixj] = ti;
+          }
+        }
+      }
+      __syncthreads();
+    }
+  }
+}
+
+__global__ void __launch_bounds__(FB_THREADS)
+knn_fallback_kernel(const float* __restrict__ X, const float* __restrict__ Xt, int64_t n_points, int d, int64_t q0,
+                    int k, const int32_t* __restrict__ work_q, const double* __restrict__ work_ub,
+                    const unsigned long long* __restrict__ work_cnt, int32_t* __restrict__ idx_out,
+                    double* __restrict__ dist_out) {
+  __shared__ double keys[FB_BUF];
+  __shared__ int32_t ids[FB_BUF];
+  __shared__ double qx[256];
+  __shared__ int cnt;
+  __shared__ double thr_key;
+  __shared__ int32_t thr_id;
+  const unsigned long long nwork = *work_cnt;
+  for (unsigned long long w = blockIdx.x; w < nwork; w += gridDim.x) {
+    const int64_t ql = work_q[w];
+    const int64_t q = q0 + ql;
+    __syncthreads();
+    for (int j = threadIdx.x; j < d; j += blockDim.x) qx[j] = X[q * d + j];
+    if (threadIdx.x == 0) {
+      cnt = 0;
+      thr_key = work_ub[w];
+      thr_id = INT32_MAX;
+    }
+    __syncthreads();
+    for (int64_t base = 0; base < n_points; base += FB_THREADS) {
+      const int64_t p = base + threadIdx.x;
+      if (p < n_points) {
+        const float* col = Xt + (p / TILE) * (int64_t)(d + 1) * TILE + (p % TILE);
+        double acc = 0.0;
+        for (int j = 0; j < d; ++j) {
+          const double df = qx[j] - (double)col[(int64_t)j * TILE];
+          acc = fma(df, df, acc);
+        }
+        const double key = (p == q) ? -1.0 : acc;
+        if (key < thr_key || (key == thr_key && (int32_t)p <= thr_id)) {
+          const int pos = atomicAdd(&cnt, 1);
+          keys[pos] = key;
+          ids[pos] = (int32_t)p;
+        }
+      }
+      __syncthreads();
+      if (cnt > FB_BUF - FB_THREADS) {
+        const int c0 = cnt;
+        for (int i = c0 + threadIdx.x; i < FB_BUF; i += blockDim.x) { keys[i] = DBL_MAX; ids[i] = INT32_MAX; }
+        __syncthreads();
+        block_bitonic_sort(keys, ids, FB_BUF);
+        if (threadIdx.x == 0) {
+          cnt = k;
+          thr_key = keys[k - 1];
+          thr_id = ids[k - 1];
+        }
+        __syncthreads();
+      }
+    }
+    const int c0 = cnt;
+    for (int i = c0 + threadIdx.x; i < FB_BUF; i += blockDim.x) { keys[i] = DBL_MAX; ids[i] = INT32_MAX; }
+    __syncthreads();
+    block_bitonic_sort(keys, ids, FB_BUF);
+    for (int i = threadIdx.x; i < k; i += blockDim.x) {
+      idx_out[ql * k + i] = ids[i];
+      dist_out[ql * k + i] = keys[i] < 0.0 ? 0.0 : sqrt(keys[i]);
+    }
+  }
+}
+
+}  // namespace
+
+extern "C" int32_t sb2_knn_l2_f32(sb2_ctx* ctx, int64_t n_points, int32_t d, const float* d_x, int64_t q0,
+                                  int64_t n_query, int32_t k, int32_t* d_idx, double* d_dist, sb2_knn_info* info) {
+  SB2_CHECK_ARG(ctx && d_x && d_idx && d_dist, "null pointer");
+  SB2_CHECK_ARG(n_points >= 1 && n_points < (int64_t)INT32_MAX - TILE, "n_points");
+  SB2_CHECK_ARG(d >= 1 && d <= 256, "d must be in [1,256]");
+  SB2_CHECK_ARG(k >= 1 && k <= LISTM - 2 && k <= n_points, "k must be in [1,30] and <= n_points");
+  SB2_CHECK_ARG(q0 >= 0 && n_query >= 0 && q0 + n_query <= n_points, "query range");
+  SB2_CHECK_ARG(q0 % TILE == 0, "q0 must be a multiple of 128");
+  if (n_query == 0) return SB2_OK;
+  SB2_CUDA(cudaSetDevice(ctx->device));
+  cudaStream_t st = ctx->stream;
+  ScratchScope scr(ctx);
+  const int64_t n_tiles = ceil_div64(n_points, TILE);
+  const int64_t chunk_f = (int64_t)(d + 1) * TILE;
+  float* Xt;
+  unsigned int* maxnorm;
+  float* cand_score;
+  int32_t* cand_idx;
+  int32_t* work_q;
+  double* work_ub;
+  unsigned long long* work_cnt;
+  SB2_TRY(scr.alloc(&Xt, (size_t)(n_tiles * chunk_f)));
+  SB2_TRY(scr.alloc(&maxnorm, 4));
+  SB2_TRY(scr.alloc(&cand_score, (size_t)n_query * LISTM));
+  SB2_TRY(scr.alloc(&cand_idx, (size_t)n_query * LISTM));
+  SB2_TRY(scr.alloc(&work_q, (size_t)n_query));
+  SB2_TRY(scr.alloc(&work_ub, (size_t)n_query));
+  SB2_TRY(scr.alloc(&work_cnt, 2));
+  SB2_CUDA(cudaMemsetAsync(maxnorm, 0, 16, st));
+  SB2_CUDA(cudaMemsetAsync(work_cnt, 0, 16, st));
+
+  {
+    size_t smem = (size_t)TILE * d * sizeof(float);
+    SB2_CUDA(cudaFuncSetAttribute(knn_prep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    knn_prep_kernel<<<(unsigned)n_tiles, 256, smem, st>>>(d_x, n_points, d, Xt, maxnorm);
+    SB2_LAUNCH_CHECK(ctx);
+  }
+  {
+    const int64_t q_tiles = ceil_div64(n_query, TILE);
+    const size_t chunk_b = (size_t)chunk_f * 4;
+    const size_t smem3 = chunk_b * 4 + 64, smem2 = chunk_b * 3 + 64;
+    const size_t lim = ctx->prop.sharedMemPerBlockOptin;
+    if (smem3 <= lim) {
+      SB2_CUDA(cudaFuncSetAttribute(knn_pass1_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem3));
+      knn_pass1_kernel<3><<<(unsigned)q_tiles, PASS1_THREADS, smem3, st>>>(Xt, d, n_tiles, q0 / TILE, n_query,
+                                                                           cand_score, cand_idx);
+    } else {
+      SB2_CHECK_ARG(smem2 <= lim, "d too large for shared memory");
+      SB2_CUDA(cudaFuncSetAttribute(knn_pass1_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
+      knn_pass1_kernel<2><<<(unsigned)q_tiles, PASS1_THREADS, smem2, st>>>(Xt, d, n_tiles, q0 / TILE, n_query,
+                                                                           cand_score, cand_idx);
+    }
+    SB2_LAUNCH_CHECK(ctx);
+  }
+  {
+    const int wpb = 8;
+    knn_rescore_kernel<<<(unsigned)ceil_div64(n_query, wpb), wpb * 32, 0, st>>>(
+        d_x, n_points, d, q0, n_query, k, cand_score, cand_idx, maxnorm, d_idx, d_dist, work_q, work_ub, work_cnt);
+    SB2_LAUNCH_CHECK(ctx);
+  }
+  {
+    const int grid = ctx->prop.multiProcessorCount * 4;
+    knn_fallback_kernel<<<grid, FB_THREADS, 0, st>>>(d_x, Xt, n_points, d, q0, k, work_q, work_ub, work_cnt, d_idx,
+                                                     d_dist);
+    SB2_LAUNCH_CHECK(ctx);
+  }
+  if (info) {
+    unsigned long long h_cnt = 0;
+    unsigned int h_bits = 0;
+    SB2_CUDA(cudaMemcpyAsync(&h_cnt, work_cnt, sizeof(h_cnt), cudaMemcpyDeviceToHost, st));
+    SB2_CUDA(cudaMemcpyAsync(&h_bits, maxnorm, sizeof(h_bits), cudaMemcpyDeviceToHost, st));
+    SB2_CUDA(cudaStreamSynchronize(st));
+    info->n_uncertified = (int64_t)h_cnt;
+    float f;
+    memcpy(&f, &h_bits, 4);
+    info->max_norm = sqrtf(f);
+  }
+  return SB2_OK;
+}

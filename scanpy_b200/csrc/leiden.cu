@@ -1,0 +1,662 @@
+// leiden.cu — Leiden community detection on a symmetric weighted CSR graph (sm_100a).
+//
+// Replaces leidenalg.find_partition(RBConfigurationVertexPartition) / igraph community_leiden as
+// called by the reference at src/scanpy/tools/_leiden.py:184-187,195-196 (and eliminates the Python
+// tuple-list graph build of src/scanpy/_utils/__init__.py:278-306: the CSR is consumed directly).
+// Objective:  Q = 1/(2m) sum_c [ sum_{i,j in c} A_ij - gamma K_c^2 / (2m) ].
+//
+// One Leiden pass = repeat { local moving -> refinement -> aggregation } until nothing merges:
+//   decide_kernel<false>  warp per vertex: weights towards neighbouring communities are summed in
+//                         registers (degree <= 32: one neighbour per lane, 32-step shuffle reduce
+//                         by community id) or in the vertex's own slice of a global hash scratch
+//                         (hubs, aggregated levels); best gain  w(v,c) - gamma k_v K_c / 2m.
+//   lm_apply_kernel       applies the decided moves, updates K_c with integer atomics, re-activates
+//                         the neighbours of moved vertices.
+//   decide_kernel<true>   refinement: singleton vertices merge into refined communities inside their
+//                         parent community; singleton->singleton merges only towards a smaller id
+//                         whose owner stays put, so refined communities stay connected.
+//   agg_* kernels         refined communities become super-vertices: per-super-vertex open-addressing
+//                         hash slices (capacity = sum of member degrees) accumulate the edge weights.
+// Determinism: moves are decided against a snapshot and applied in a separate kernel; every
+// accumulated quantity (edge weights, strengths K_c) is a 2^-32 fixed-point int64, so atomic order
+// cannot change any sum; ties break towards the smaller community id.  Same seed => same labels.
+// HBM-bound integer/gather work; per local-move sweep ~ 12*E (idx + weight) + 4*E (community gather) B.
+#include <math.h>
+#include <string.h>
+
+#include <algorithm>
+#include <vector>
+
+#include "common.cuh"
+
+namespace {
+
+typedef unsigned long long u64;
+constexpr double FX = 4294967296.0;  // 2^32 fixed-point scale
+
+struct Level {
+  int32_t n;
+  const int64_t* indptr;
+  const int32_t* indices;
+  const int64_t* w;  // fixed-point arc weights
+  int64_t* k;        // fixed-point strengths (incl. self loops)
+};
+
+__host__ __device__ __forceinline__ uint32_t mix32(uint32_t x) {
+  x ^= x >> 16; x *= 0x7feb352dU; x ^= x >> 15; x *= 0x846ca68bU; x ^= x >> 16;
+  return x;
+}
+
+__global__ void to_fixed_kernel(const float* __restrict__ w, int64_t n, int64_t* __restrict__ out) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = llrint((double)w[i] * FX);
+}
+__global__ void strength_kernel(int32_t n, const int64_t* __restrict__ indptr, const int64_t* __restrict__ w,
+                                int64_t* __restrict__ k, u64* __restrict__ total) {
+  const int32_t v = blockIdx.x * blockDim.x + threadIdx.x;
+  int64_t s = 0;
+  if (v < n) {
+    for (int64_t e = indptr[v]; e < indptr[v + 1]; ++e) s += w[e];
+    k[v] = s;
+  }
+  // block reduce -> one atomic
+  __shared__ long long red[8];
+  long long x = s;
+  for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = x;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    long long t = 0;
+    for (int i = 0; i < (int)(blockDim.x >> 5); ++i) t += red[i];
+    atomicAdd(total, (u64)t);
+  }
+}
+__global__ void comm_stats_kernel(int32_t n, const int32_t* __restrict__ comm, const int64_t* __restrict__ k,
+                                  u64* __restrict__ K, int32_t* __restrict__ csize) {
+  const int32_t v = blockIdx.x * blockDim.x + threadIdx.x;
+  if (v >= n) return;
+  atomicAdd(&K[comm[v]], (u64)k[v]);
+  atomicAdd(&csize[comm[v]], 1);
+}
+__global__ void iota_kernel(int32_t* __restrict__ a, int64_t n) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) a[i] = (int32_t)i;
+}
+__global__ void fill_u8_kernel(uint8_t* __restrict__ a, int64_t n, uint8_t v) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) a[i] = v;
+}
+
+// ---------------------------------------------------------------------------------------------
+// REFINE=false: local moving.  key(u) = comm[u];  stay gain uses K[a]-k_v.
+// REFINE=true : refinement.    only singleton v (rsize[ref[v]]==1); neighbours restricted to the same
+//               parent community; key(u) = ref[u]; stay gain = 0.
+// target[v]: >=0 move to that community, -1 stay (and deactivate), -2 skipped this sweep (stay active)
+template <bool REFINE>
+__global__ void __launch_bounds__(256)
+decide_kernel(Level L, const int32_t* __restrict__ comm, const int32_t* __restrict__ ref,
+              const int64_t* __restrict__ K, const int32_t* __restrict__ csize, const uint8_t* __restrict__ active,
+              double gamma, double total, uint32_t seed, int sweep, int noskip, int32_t* __restrict__ hkeys,
+              int64_t* __restrict__ hvals, int32_t* __restrict__ target, uint8_t* __restrict__ tsingle) {
+  const int lane = threadIdx.x & 31;
+  const int32_t v = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (v >= L.n) return;
+  if (!REFINE) {
+    if (!active[v]) { if (lane == 0) target[v] = -1; return; }
+    if (!noskip) {
+      const uint32_t bit = (mix32((uint32_t)v * 0x9E3779B9U + seed * 0x85EBCA6BU + (uint32_t)(sweep >> 1)) + (uint32_t)sweep) & 1u;
+      if (bit) { if (lane == 0) target[v] = -2; return; }
+    }
+  } else {
+    if (csize[ref[v]] != 1) { if (lane == 0) target[v] = -1; return; }
+  }
+  const int64_t e0 = L.indptr[v], e1 = L.indptr[v + 1];
+  const int deg = (int)(e1 - e0);
+  const int32_t a = REFINE ? ref[v] : comm[v];
+  const int32_t pv = comm[v];
+  const double kv = (double)L.k[v];
+  const double scale = gamma * kv / total;
+  double best_gain = -1e300;
+  int32_t best = -1;
+  double wa = 0.0;  // weight towards own community (local moving only)
+
+  if (deg <= 32) {
+    int32_t c = -1 - lane;  // unique negative = "no neighbour"
+    int64_t w = 0;
+    if (lane < deg) {
+      const int32_t u = L.indices[e0 + lane];
+      if (u != v && (!REFINE || comm[u] == pv)) {
+        c = REFINE ? ref[u] : comm[u];
+        w = L.w[e0 + lane];
+      }
+    }
+    int64_t tot = 0;
+    bool leader = true;
+#pragma unroll
+    for (int s = 0; s < 32; ++s) {
+      const int32_t cs = __shfl_sync(0xffffffffu, c, s);
+      const int64_t ws = __shfl_sync(0xffffffffu, w, s);
+      if (cs == c) {
+        tot += ws;
+        if (s < lane) leader = false;
+      }
+    }
+    if (c >= 0 && leader) {
+      if (!REFINE && c == a) wa = (double)tot;
+      else { best_gain = (double)tot - scale * (double)K[c]; best = c; }
+    }
+  } else {
+    // hash slice [e0, e1): capacity = deg >= number of distinct neighbouring communities
+    for (int64_t s = e0 + lane; s < e1; s += 32) { hkeys[s] = -1; hvals[s] = 0; }
+    __syncwarp();
+    for (int64_t e = e0 + lane; e < e1; e += 32) {
+      const int32_t u = L.indices[e];
+      if (u == v || (REFINE && comm[u] != pv)) continue;
+      const int32_t c = REFINE ? ref[u] : comm[u];
+      uint32_t slot = mix32((uint32_t)c) % (uint32_t)deg;
+      for (;;) {
+        const int32_t prev = atomicCAS(&hkeys[e0 + slot], -1, c);
+        if (prev == -1 || prev == c) { atomicAdd((u64*)&hvals[e0 + slot], (u64)L.w[e]); break; }
+        slot = slot + 1 == (uint32_t)deg ? 0 : slot + 1;
+      }
+    }
+    __syncwarp();
+    for (int64_t s = e0 + lane; s < e1; s += 32) {
+      const int32_t c = hkeys[s];
+      if (c < 0) continue;
+      const double tot = (double)hvals[s];
+      if (!REFINE && c == a) { wa = tot; continue; }
+      const double gain = tot - scale * (double)K[c];
+      if (gain > best_gain || (gain == best_gain && c < best)) { best_gain = gain; best = c; }
+    }
+  }
+  // warp arg-max (gain desc, id asc); own-community weight summed (only one lane holds it)
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const double og = __shfl_xor_sync(0xffffffffu, best_gain, o);
+    const int32_t ob = __shfl_xor_sync(0xffffffffu, best, o);
+    const double owa = __shfl_xor_sync(0xffffffffu, wa, o);
+    wa += owa;
+    if (ob >= 0 && (best < 0 || og > best_gain || (og == best_gain && ob < best))) { best_gain = og; best = ob; }
+  }
+  if (lane == 0) {
+    int32_t t = -1;
+    uint8_t ts = 0;
+    if (best >= 0) {
+      const double stay = REFINE ? 0.0 : wa - scale * ((double)K[a] - kv);
+      if (best_gain > stay + 0.5) {
+        const bool bsingle = csize[best] == 1;
+        if (!REFINE) {
+          // swap guard: two singletons may only merge towards the smaller community id
+          if (!(csize[a] == 1 && bsingle && best > a)) t = best;
+        } else {
+          if (!(bsingle && best > v)) { t = best; ts = bsingle ? 1 : 0; }
+        }
+      }
+    }
+    target[v] = t;
+    if (REFINE) tsingle[v] = ts;
+  }
+}
+
+__global__ void lm_apply_kernel(Level L, int32_t* __restrict__ comm, const int32_t* __restrict__ target,
+                                u64* __restrict__ K, int32_t* __restrict__ csize, uint8_t* __restrict__ active_next,
+                                u64* __restrict__ moves) {
+  const int32_t v = blockIdx.x * blockDim.x + threadIdx.x;
+  if (v >= L.n) return;
+  const int32_t t = target[v];
+  if (t == -2) { active_next[v] = 1; return; }
+  if (t < 0) return;
+  const int32_t a = comm[v];
+  const u64 kv = (u64)L.k[v];
+  comm[v] = t;
+  atomicAdd(&K[a], (u64)0 - kv);
+  atomicAdd(&K[t], kv);
+  atomicAdd(&csize[a], -1);
+  atomicAdd(&csize[t], 1);
+  for (int64_t e = L.indptr[v]; e < L.indptr[v + 1]; ++e) active_next[L.indices[e]] = 1;
+  atomicAdd(moves, 1ull);
+}
+
+__global__ void rf_init_kernel(int32_t n, const int64_t* __restrict__ k, int32_t* __restrict__ ref,
+                               int64_t* __restrict__ Kref, int32_t* __restrict__ rsize) {
+  const int32_t v = blockIdx.x * blockDim.x + threadIdx.x;
+  if (v >= n) return;
+  ref[v] = v;
+  Kref[v] = k[v];
+  rsize[v] = 1;
+}
+__global__ void rf_apply_kernel(int32_t n, const int64_t* __restrict__ k, const int32_t* __restrict__ target,
+                                const uint8_t* __restrict__ tsingle, int32_t* __restrict__ ref, u64* __restrict__ Kref,
+                                int32_t* __restrict__ rsize, u64* __restrict__ merges) {
+  const int32_t v = blockIdx.x * blockDim.x + threadIdx.x;
+  if (v >= n) return;
+  const int32_t t = target[v];
+  if (t < 0) return;
+  // a singleton target (label == vertex id) must itself stay put, otherwise v would join an abandoned label
+  if (tsingle[v] && target[t] >= 0) return;
+  ref[v] = t;
+  atomicAdd(&Kref[t], (u64)k[v]);
+  Kref[v] = 0;
+  atomicAdd(&rsize[t], 1);
+  rsize[v] = 0;
+  atomicAdd(merges, 1ull);
+}
+
+// ---------------------------------------------------------------------------------------------
+// aggregation
+__global__ void flag_nonempty_kernel(int32_t n, const int32_t* __restrict__ rsize, int32_t* __restrict__ flag) {
+  const int32_t v = blockIdx.x * blockDim.x + threadIdx.x;
+  if (v < n) flag[v] = rsize[v] > 0 ? 1 : 0;
+}
+__global__ void agg_map_kernel(int32_t n, const int32_t* __restrict__ ref, const int64_t* __restrict__ newid_scan,
+                               const int32_t* __restrict__ comm, const int64_t* __restrict__ indptr,
+                               int32_t* __restrict__ rnew, int32_t* __restrict__ comm_new, int32_t* __restrict__ degsum) {
+  const int32_t v = blockIdx.x * blockDim.x + threadIdx.x;
+  if (v >= n) return;
+  const int32_t r = (int32_t)newid_scan[ref[v]];
+  rnew[v] = r;
+  comm_new[r] = comm[v];  // all members share the parent community
+  atomicAdd(&degsum[r], (int32_t)(indptr[v + 1] - indptr[v]));
+}
+__global__ void agg_clear_kernel(int64_t n, int32_t* __restrict__ hkeys, int64_t* __restrict__ hvals) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) { hkeys[i] = -1; hvals[i] = 0; }
+}
+__global__ void __launch_bounds__(256)
+agg_insert_kernel(Level L, const int32_t* __restrict__ rnew, const int64_t* __restrict__ slice,
+                  int32_t* __restrict__ hkeys, int64_t* __restrict__ hvals) {
+  const int lane = threadIdx.x & 31;
+  const int32_t v = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (v >= L.n) return;
+  const int32_t r = rnew[v];
+  const int64_t s0 = slice[r];
+  const uint32_t cap = (uint32_t)(slice[r + 1] - s0);
+  for (int64_t e = L.indptr[v] + lane; e < L.indptr[v + 1]; e += 32) {
+    const int32_t c = rnew[L.indices[e]];
+    uint32_t slot = mix32((uint32_t)c) % cap;
+    for (;;) {
+      const int32_t prev = atomicCAS(&hkeys[s0 + slot], -1, c);
+      if (prev == -1 || prev == c) { atomicAdd((u64*)&hvals[s0 + slot], (u64)L.w[e]); break; }
+      slot = slot + 1 == cap ? 0 : slot + 1;
+    }
+  }
+}
+__global__ void __launch_bounds__(256)
+agg_count_kernel(int32_t nc, const int64_t* __restrict__ slice, const int32_t* __restrict__ hkeys,
+                 int32_t* __restrict__ cnt) {
+  const int lane = threadIdx.x & 31;
+  const int32_t r = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (r >= nc) return;
+  int c = 0;
+  for (int64_t s = slice[r] + lane; s < slice[r + 1]; s += 32) c += hkeys[s] >= 0;
+  for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+  if (lane == 0) cnt[r] = c;
+}
+__global__ void __launch_bounds__(256)
+agg_fill_kernel(int32_t nc, const int64_t* __restrict__ slice, const int32_t* __restrict__ hkeys,
+                const int64_t* __restrict__ hvals, const int64_t* __restrict__ indptr_new,
+                int32_t* __restrict__ indices_new, int64_t* __restrict__ w_new) {
+  const int lane = threadIdx.x & 31;
+  const int32_t r = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (r >= nc) return;
+  int64_t out = indptr_new[r];
+  for (int64_t s0 = slice[r]; s0 < slice[r + 1]; s0 += 32) {
+    const int64_t s = s0 + lane;
+    const bool has = s < slice[r + 1] && hkeys[s] >= 0;
+    const unsigned m = __ballot_sync(0xffffffffu, has);
+    if (has) {
+      const int64_t p = out + __popc(m & ((1u << lane) - 1u));
+      indices_new[p] = hkeys[s];
+      w_new[p] = hvals[s];
+    }
+    out += __popc(m);
+  }
+}
+__global__ void compose_kernel(int64_t n0, int32_t* __restrict__ node_of, const int32_t* __restrict__ rnew) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n0) node_of[i] = rnew[node_of[i]];
+}
+__global__ void gather_kernel(int64_t n0, const int32_t* __restrict__ node_of, const int32_t* __restrict__ comm,
+                              int32_t* __restrict__ out) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n0) out[i] = comm[node_of[i]];
+}
+
+// ---------------------------------------------------------------------------------------------
+// modularity pieces and final renumbering
+__global__ void internal_weight_kernel(int32_t n, const int64_t* __restrict__ indptr, const int32_t* __restrict__ indices,
+                                       const int64_t* __restrict__ w, const int32_t* __restrict__ comm,
+                                       u64* __restrict__ internal) {
+  const int32_t v = blockIdx.x * blockDim.x + threadIdx.x;
+  long long s = 0;
+  if (v < n) {
+    const int32_t c = comm[v];
+    for (int64_t e = indptr[v]; e < indptr[v + 1]; ++e)
+      if (comm[indices[e]] == c) s += w[e];
+  }
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if ((threadIdx.x & 31) == 0 && s != 0) atomicAdd(internal, (u64)s);
+}
+__global__ void comm_min_member_kernel(int64_t n, const int32_t* __restrict__ comm, int32_t* __restrict__ minmem) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) atomicMin(&minmem[comm[i]], (int32_t)i);
+}
+__global__ void relabel_kernel(int64_t n, int32_t* __restrict__ comm, const int32_t* __restrict__ newid) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) comm[i] = newid[comm[i]];
+}
+
+struct Work {
+  sb2_ctx* ctx;
+  cudaStream_t st;
+  int32_t n0;
+  u64* K;          // [n0]
+  int32_t* csize;  // [n0]
+  int32_t* hkeys;  // [E0]
+  int64_t* hvals;  // [E0]
+  int32_t* target; // [n0]
+  uint8_t* tsingle;
+  uint8_t* active[2];
+  u64* counter;    // device counters [4]
+  double gamma;
+  double total;    // 2m in fixed units
+  uint32_t seed;
+  int64_t moves_total;
+};
+
+inline unsigned gridw(int64_t n) { return (unsigned)ceil_div64(n, 8); }    // warp per item, 8 warps/CTA
+inline unsigned gridt(int64_t n) { return (unsigned)ceil_div64(n, 256); }  // thread per item
+
+int32_t read_counter(Work& w, int idx, u64* out) {
+  SB2_CUDA(cudaMemcpyAsync(out, w.counter + idx, sizeof(u64), cudaMemcpyDeviceToHost, w.st));
+  SB2_CUDA(cudaStreamSynchronize(w.st));
+  return SB2_OK;
+}
+
+int32_t local_move(Work& w, const Level& L, int32_t* comm, int64_t* moves_out) {
+  sb2_ctx* ctx = w.ctx;
+  SB2_CUDA(cudaMemsetAsync(w.K, 0, sizeof(u64) * w.n0, w.st));
+  SB2_CUDA(cudaMemsetAsync(w.csize, 0, sizeof(int32_t) * w.n0, w.st));
+  comm_stats_kernel<<<gridt(L.n), 256, 0, w.st>>>(L.n, comm, L.k, w.K, w.csize);
+  SB2_LAUNCH_CHECK(ctx);
+  fill_u8_kernel<<<gridt(L.n), 256, 0, w.st>>>(w.active[0], L.n, 1);
+  SB2_LAUNCH_CHECK(ctx);
+  int cur = 0, noskip = 0;
+  int64_t moves = 0;
+  const int max_sweeps = 200;
+  for (int sweep = 0; sweep < max_sweeps; ++sweep) {
+    SB2_CUDA(cudaMemsetAsync(w.active[cur ^ 1], 0, (size_t)L.n, w.st));
+    SB2_CUDA(cudaMemsetAsync(w.counter, 0, sizeof(u64), w.st));
+    decide_kernel<false><<<gridw(L.n), 256, 0, w.st>>>(L, comm, nullptr, (const int64_t*)w.K, w.csize, w.active[cur], w.gamma,
+                                                       w.total, w.seed, sweep, noskip, w.hkeys, w.hvals, w.target, nullptr);
+    SB2_LAUNCH_CHECK(ctx);
+    lm_apply_kernel<<<gridt(L.n), 256, 0, w.st>>>(L, comm, w.target, w.K, w.csize, w.active[cur ^ 1], w.counter);
+    SB2_LAUNCH_CHECK(ctx);
+    u64 c = 0;
+    SB2_TRY(read_counter(w, 0, &c));
+    moves += (int64_t)c;
+    cur ^= 1;
+    if (c == 0) {
+      if (noskip) break;
+      noskip = 1;  // confirm with a sweep in which every active vertex decides
+    } else {
+      noskip = 0;
+    }
+  }
+  *moves_out = moves;
+  return SB2_OK;
+}
+
+int32_t refine(Work& w, const Level& L, const int32_t* comm, int32_t* ref, int64_t* Kref, int32_t* rsize) {
+  sb2_ctx* ctx = w.ctx;
+  rf_init_kernel<<<gridt(L.n), 256, 0, w.st>>>(L.n, L.k, ref, Kref, rsize);
+  SB2_LAUNCH_CHECK(ctx);
+  for (int round = 0; round < 64; ++round) {
+    SB2_CUDA(cudaMemsetAsync(w.counter, 0, sizeof(u64), w.st));
+    decide_kernel<true><<<gridw(L.n), 256, 0, w.st>>>(L, comm, ref, Kref, rsize, nullptr, w.gamma, w.total, w.seed, round, 1,
+                                                      w.hkeys, w.hvals, w.target, w.tsingle);
+    SB2_LAUNCH_CHECK(ctx);
+    rf_apply_kernel<<<gridt(L.n), 256, 0, w.st>>>(L.n, L.k, w.target, w.tsingle, ref, (u64*)Kref, rsize, w.counter);
+    SB2_LAUNCH_CHECK(ctx);
+    u64 c = 0;
+    SB2_TRY(read_counter(w, 0, &c));
+    if (c == 0) break;
+  }
+  return SB2_OK;
+}
+
+}  // namespace
+
+// quality of `comm` (labels < n) on the level-0 fixed-point graph; K/csize scratch sized n
+static int32_t quality_device(sb2_ctx* ctx, ScratchScope& scr, int32_t n, const int64_t* indptr, const int32_t* indices,
+                              const int64_t* wfx, const int64_t* kfx, double total, double gamma, const int32_t* comm,
+                              double* q_out) {
+  cudaStream_t st = ctx->stream;
+  u64* K;
+  int32_t* csize;
+  u64* internal;
+  SB2_TRY(scr.alloc(&K, (size_t)n));
+  SB2_TRY(scr.alloc(&csize, (size_t)n));
+  SB2_TRY(scr.alloc(&internal, 2));
+  SB2_CUDA(cudaMemsetAsync(K, 0, sizeof(u64) * n, st));
+  SB2_CUDA(cudaMemsetAsync(csize, 0, sizeof(int32_t) * n, st));
+  SB2_CUDA(cudaMemsetAsync(internal, 0, 16, st));
+  comm_stats_kernel<<<gridt(n), 256, 0, st>>>(n, comm, kfx, K, csize);
+  SB2_LAUNCH_CHECK(ctx);
+  internal_weight_kernel<<<gridt(n), 256, 0, st>>>(n, indptr, indices, wfx, comm, internal);
+  SB2_LAUNCH_CHECK(ctx);
+  std::vector<u64> hK((size_t)n);
+  u64 hin = 0;
+  SB2_CUDA(cudaMemcpyAsync(hK.data(), K, sizeof(u64) * n, cudaMemcpyDeviceToHost, st));
+  SB2_CUDA(cudaMemcpyAsync(&hin, internal, sizeof(u64), cudaMemcpyDeviceToHost, st));
+  SB2_CUDA(cudaStreamSynchronize(st));
+  if (total <= 0.0) { *q_out = 0.0; return SB2_OK; }
+  double pen = 0.0;
+  for (int32_t c = 0; c < n; ++c) {
+    const double kc = (double)(long long)hK[c];
+    pen += kc * kc;
+  }
+  *q_out = ((double)(long long)hin - gamma * pen / total) / total;
+  return SB2_OK;
+}
+
+// renumber labels (< n) by decreasing size, ties -> smaller first member; returns #communities
+static int32_t renumber_device(sb2_ctx* ctx, ScratchScope& scr, int64_t n, int32_t* comm, int32_t* n_comms) {
+  cudaStream_t st = ctx->stream;
+  int32_t *minmem, *newid;
+  SB2_TRY(scr.alloc(&minmem, (size_t)n));
+  SB2_TRY(scr.alloc(&newid, (size_t)n));
+  SB2_CUDA(cudaMemsetAsync(minmem, 0x7f, sizeof(int32_t) * n, st));
+  comm_min_member_kernel<<<gridt(n), 256, 0, st>>>(n, comm, minmem);
+  SB2_LAUNCH_CHECK(ctx);
+  std::vector<int32_t> hcomm((size_t)n), hmin((size_t)n);
+  SB2_CUDA(cudaMemcpyAsync(hcomm.data(), comm, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, st));
+  SB2_CUDA(cudaMemcpyAsync(hmin.data(), minmem, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, st));
+  SB2_CUDA(cudaStreamSynchronize(st));
+  std::vector<int64_t> size((size_t)n, 0);
+  for (int64_t i = 0; i < n; ++i) size[hcomm[i]]++;
+  std::vector<int32_t> ids;
+  for (int64_t c = 0; c < n; ++c)
+    if (size[c] > 0) ids.push_back((int32_t)c);
+  std::sort(ids.begin(), ids.end(), [&](int32_t a, int32_t b) {
+    if (size[a] != size[b]) return size[a] > size[b];
+    return hmin[a] < hmin[b];
+  });
+  std::vector<int32_t> hnew((size_t)n, -1);
+  for (size_t r = 0; r < ids.size(); ++r) hnew[ids[r]] = (int32_t)r;
+  SB2_CUDA(cudaMemcpyAsync(newid, hnew.data(), sizeof(int32_t) * n, cudaMemcpyHostToDevice, st));
+  relabel_kernel<<<gridt(n), 256, 0, st>>>(n, comm, newid);
+  SB2_LAUNCH_CHECK(ctx);
+  SB2_CUDA(cudaStreamSynchronize(st));
+  *n_comms = (int32_t)ids.size();
+  return SB2_OK;
+}
+
+static int32_t prepare_level0(sb2_ctx* ctx, ScratchScope& scr, int64_t n, const int64_t* d_indptr, const float* d_weights,
+                              int64_t* nnz_out, int64_t** wfx, int64_t** kfx, double* total) {
+  cudaStream_t st = ctx->stream;
+  int64_t nnz = 0;
+  SB2_CUDA(cudaMemcpyAsync(&nnz, d_indptr + n, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+  SB2_CUDA(cudaStreamSynchronize(st));
+  *nnz_out = nnz;
+  SB2_TRY(scr.alloc(wfx, (size_t)nnz));
+  SB2_TRY(scr.alloc(kfx, (size_t)n));
+  u64* tot;
+  SB2_TRY(scr.alloc(&tot, 2));
+  SB2_CUDA(cudaMemsetAsync(tot, 0, 16, st));
+  if (nnz > 0) {
+    to_fixed_kernel<<<gridt(nnz), 256, 0, st>>>(d_weights, nnz, *wfx);
+    SB2_LAUNCH_CHECK(ctx);
+  }
+  strength_kernel<<<gridt(n), 256, 0, st>>>((int32_t)n, d_indptr, *wfx, *kfx, tot);
+  SB2_LAUNCH_CHECK(ctx);
+  u64 ht = 0;
+  SB2_CUDA(cudaMemcpyAsync(&ht, tot, sizeof(u64), cudaMemcpyDeviceToHost, st));
+  SB2_CUDA(cudaStreamSynchronize(st));
+  *total = (double)(long long)ht;
+  return SB2_OK;
+}
+
+extern "C" int32_t sb2_modularity_csr_f32(sb2_ctx* ctx, int64_t n, const int64_t* d_indptr, const int32_t* d_indices,
+                                          const float* d_weights, double resolution, const int32_t* d_membership,
+                                          double* h_modularity) {
+  SB2_CHECK_ARG(ctx && d_indptr && d_indices && d_weights && d_membership && h_modularity, "null pointer");
+  SB2_CHECK_ARG(n >= 1 && n < INT32_MAX, "n");
+  SB2_CUDA(cudaSetDevice(ctx->device));
+  ScratchScope scr(ctx);
+  int64_t nnz, *wfx, *kfx;
+  double total;
+  SB2_TRY(prepare_level0(ctx, scr, n, d_indptr, d_weights, &nnz, &wfx, &kfx, &total));
+  // labels may be arbitrary non-negative ints < n
+  return quality_device(ctx, scr, (int32_t)n, d_indptr, d_indices, wfx, kfx, total, resolution, d_membership, h_modularity);
+}
+
+extern "C" int32_t sb2_leiden_csr_f32(sb2_ctx* ctx, int64_t n, const int64_t* d_indptr, const int32_t* d_indices,
+                                      const float* d_weights, double resolution, int32_t n_iterations, uint64_t seed,
+                                      int32_t* d_membership, double* h_modularity, int32_t* h_n_comms,
+                                      sb2_leiden_info* info) {
+  SB2_CHECK_ARG(ctx && d_indptr && d_indices && d_weights && d_membership && h_modularity && h_n_comms, "null pointer");
+  SB2_CHECK_ARG(n >= 1 && n < INT32_MAX, "n");
+  SB2_CHECK_ARG(resolution >= 0.0, "resolution");
+  SB2_CUDA(cudaSetDevice(ctx->device));
+  cudaStream_t st = ctx->stream;
+  ScratchScope scr(ctx);
+  const int32_t n0 = (int32_t)n;
+  int64_t nnz0, *wfx0, *kfx0;
+  double total;
+  SB2_TRY(prepare_level0(ctx, scr, n, d_indptr, d_weights, &nnz0, &wfx0, &kfx0, &total));
+
+  Work w{};
+  w.ctx = ctx; w.st = st; w.n0 = n0; w.gamma = resolution; w.total = total;
+  w.seed = (uint32_t)(seed ^ (seed >> 32));
+  SB2_TRY(scr.alloc(&w.K, (size_t)n0));
+  SB2_TRY(scr.alloc(&w.csize, (size_t)n0));
+  SB2_TRY(scr.alloc(&w.hkeys, (size_t)std::max<int64_t>(nnz0, 1)));
+  SB2_TRY(scr.alloc(&w.hvals, (size_t)std::max<int64_t>(nnz0, 1)));
+  SB2_TRY(scr.alloc(&w.target, (size_t)n0));
+  SB2_TRY(scr.alloc(&w.tsingle, (size_t)n0));
+  SB2_TRY(scr.alloc(&w.active[0], (size_t)n0));
+  SB2_TRY(scr.alloc(&w.active[1], (size_t)n0));
+  SB2_TRY(scr.alloc(&w.counter, 4));
+  int32_t *node_of, *comm, *comm_next, *ref, *rsize, *rnew, *flag, *degsum, *cnt;
+  int64_t *Kref, *scan_tmp;
+  SB2_TRY(scr.alloc(&node_of, (size_t)n0));
+  SB2_TRY(scr.alloc(&comm, (size_t)n0));
+  SB2_TRY(scr.alloc(&comm_next, (size_t)n0));
+  SB2_TRY(scr.alloc(&ref, (size_t)n0));
+  SB2_TRY(scr.alloc(&rsize, (size_t)n0));
+  SB2_TRY(scr.alloc(&rnew, (size_t)n0));
+  SB2_TRY(scr.alloc(&flag, (size_t)n0));
+  SB2_TRY(scr.alloc(&degsum, (size_t)n0));
+  SB2_TRY(scr.alloc(&cnt, (size_t)n0));
+  SB2_TRY(scr.alloc(&Kref, (size_t)n0));
+  SB2_TRY(scr.alloc(&scan_tmp, (size_t)n0 + 1));
+  int64_t* slice;
+  SB2_TRY(scr.alloc(&slice, (size_t)n0 + 1));
+
+  iota_kernel<<<gridt(n0), 256, 0, st>>>(d_membership, n0);
+  SB2_LAUNCH_CHECK(ctx);
+
+  int passes = 0, levels = 0;
+  if (total > 0.0) {
+    for (;;) {
+      // ---- one Leiden pass starting from d_membership on the level-0 graph ----
+      Level L{n0, d_indptr, d_indices, wfx0, kfx0};
+      SB2_CUDA(cudaMemcpyAsync(comm, d_membership, sizeof(int32_t) * n0, cudaMemcpyDeviceToDevice, st));
+      iota_kernel<<<gridt(n0), 256, 0, st>>>(node_of, n0);
+      SB2_LAUNCH_CHECK(ctx);
+      int64_t pass_moves = 0;
+      levels = 0;
+      ScratchScope lvl(ctx);  // aggregated graphs of this pass
+      for (;;) {
+        int64_t mv = 0;
+        SB2_TRY(local_move(w, L, comm, &mv));
+        pass_moves += mv;
+        ++levels;
+        SB2_TRY(refine(w, L, comm, ref, Kref, rsize));
+        // compact refined labels
+        flag_nonempty_kernel<<<gridt(L.n), 256, 0, st>>>(L.n, rsize, flag);
+        SB2_LAUNCH_CHECK(ctx);
+        SB2_TRY(sb2_scan_i32_to_i64(ctx, flag, L.n, scan_tmp));
+        int64_t nc64 = 0;
+        SB2_CUDA(cudaMemcpyAsync(&nc64, scan_tmp + L.n, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+        SB2_CUDA(cudaStreamSynchronize(st));
+        const int32_t nc = (int32_t)nc64;
+        if (nc >= L.n) break;  // nothing merged: the aggregate would not shrink
+        // ---- aggregate ----
+        SB2_CUDA(cudaMemsetAsync(degsum, 0, sizeof(int32_t) * nc, st));
+        agg_map_kernel<<<gridt(L.n), 256, 0, st>>>(L.n, ref, scan_tmp, comm, L.indptr, rnew, comm_next, degsum);
+        SB2_LAUNCH_CHECK(ctx);
+        SB2_TRY(sb2_scan_i32_to_i64(ctx, degsum, nc, slice));
+        int64_t eL = 0;
+        SB2_CUDA(cudaMemcpyAsync(&eL, slice + nc, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+        SB2_CUDA(cudaStreamSynchronize(st));
+        if (eL > 0) {
+          agg_clear_kernel<<<gridt(eL), 256, 0, st>>>(eL, w.hkeys, w.hvals);
+          SB2_LAUNCH_CHECK(ctx);
+          agg_insert_kernel<<<gridw(L.n), 256, 0, st>>>(L, rnew, slice, w.hkeys, w.hvals);
+          SB2_LAUNCH_CHECK(ctx);
+        }
+        agg_count_kernel<<<gridw(nc), 256, 0, st>>>(nc, slice, w.hkeys, cnt);
+        SB2_LAUNCH_CHECK(ctx);
+        int64_t* indptr_new;
+        SB2_TRY(lvl.alloc(&indptr_new, (size_t)nc + 1));
+        SB2_TRY(sb2_scan_i32_to_i64(ctx, cnt, nc, indptr_new));
+        int64_t nnz_new = 0;
+        SB2_CUDA(cudaMemcpyAsync(&nnz_new, indptr_new + nc, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+        SB2_CUDA(cudaStreamSynchronize(st));
+        int32_t* indices_new;
+        int64_t *w_new, *k_new;
+        SB2_TRY(lvl.alloc(&indices_new, (size_t)std::max<int64_t>(nnz_new, 1)));
+        SB2_TRY(lvl.alloc(&w_new, (size_t)std::max<int64_t>(nnz_new, 1)));
+        SB2_TRY(lvl.alloc(&k_new, (size_t)nc));
+        agg_fill_kernel<<<gridw(nc), 256, 0, st>>>(nc, slice, w.hkeys, w.hvals, indptr_new, indices_new, w_new);
+        SB2_LAUNCH_CHECK(ctx);
+        SB2_CUDA(cudaMemsetAsync(w.counter + 2, 0, sizeof(u64), st));
+        strength_kernel<<<gridt(nc), 256, 0, st>>>(nc, indptr_new, w_new, k_new, w.counter + 2);
+        SB2_LAUNCH_CHECK(ctx);
+        compose_kernel<<<gridt(n0), 256, 0, st>>>(n0, node_of, rnew);
+        SB2_LAUNCH_CHECK(ctx);
+        std::swap(comm, comm_next);
+        L = Level{nc, indptr_new, indices_new, w_new, k_new};
+      }
+      gather_kernel<<<gridt(n0), 256, 0, st>>>(n0, node_of, comm, d_membership);
+      SB2_LAUNCH_CHECK(ctx);
+      SB2_CUDA(cudaStreamSynchronize(st));
+      ++passes;
+      w.moves_total += pass_moves;
+      w.seed = mix32(w.seed + 0x9E3779B9U);
+      if (n_iterations >= 0 ? passes >= n_iterations : pass_moves == 0) break;
+      if (passes >= 64) break;
+    }
+  }
+  SB2_TRY(renumber_device(ctx, scr, n, d_membership, h_n_comms));
+  SB2_TRY(quality_device(ctx, scr, n0, d_indptr, d_indices, wfx0, kfx0, total, resolution, d_membership, h_modularity));
+  if (info) {
+    info->passes = passes;
+    info->levels = levels;
+    info->moves = w.moves_total;
+  }
+  return SB2_OK;
+}

@@ -1,0 +1,803 @@
+// pca.cu — PCA of an implicitly centred CSR matrix (sm_100a).
+//
+// Replaces sklearn PCA(svd_solver='arpack') -> scipy svds -> ARPACK as called by the reference at
+// src/scanpy/preprocessing/_pca/__init__.py:282-291,308 (arithmetic spec: SURVEY.md Appendix A1),
+// and the `covariance_eigh` Gram route of src/scanpy/preprocessing/_pca/_dask.py:143-213 +
+// _pca/_kernels.py:14-58.
+//
+// Kernels (all HBM/L2-bound integer+fp32 streaming work; no tensor cores):
+//   csr_col_stats_kernel   one CSR pass: per-gene sum and sum of squares (fp64 REDs into replicated
+//                          accumulators)                                   bytes: 8*nnz + 8*(n+1)
+//   spmm_csr_kernel        Y = X*B - 1*shift^T, warp per row, lanes own l/32 columns of B;
+//                          coalesced column-index loads, shuffle-broadcast of (col,val), B rows are
+//                          read as one 128..512 B segment per non-zero     bytes: 8*nnz + 4*n*l
+//   spmm_csr_t_kernel      Z += X^T*Y, warp per row, (l/4) lanes per non-zero issue one
+//                          RED.ADD.F32x4 each into one of 8 replicated fp32 copies of Z (L2 resident)
+//   csr_gram_kernel        G += x_r x_r^T (upper triangle), warp per row, fp64 REDs into L2-resident G
+//   small dense fp64 helpers (g x l blocks, l <= 128): A^T B, A*M, C*V, residual norms.
+// Host side (C++ in this file): the block subspace iteration, CholeskyQR2 with an eigen-based
+// fallback for rank-deficient blocks, and a cyclic-Jacobi eigensolver for the l x l Rayleigh-Ritz
+// problem (l <= 128; fp64).  Centering never densifies X:  X_c B = X B - 1 (mu^T B) and, because
+// the columns of that product sum to zero, X_c^T (X_c B) = X^T (X B - 1 mu^T B).
+#include <math.h>
+#include <string.h>
+
+#include <algorithm>
+#include <vector>
+
+#include "common.cuh"
+
+namespace {
+
+constexpr int STAT_COPIES = 32;
+constexpr int ZT_COPIES = 8;
+
+// ---------------------------------------------------------------------------------------------
+__global__ void csr_col_stats_kernel(int64_t nnz, const int32_t* __restrict__ indices, const float* __restrict__ data,
+                                     int g, double* __restrict__ acc /* [COPIES][2][g] */) {
+  double* mine = acc + (size_t)(blockIdx.x % STAT_COPIES) * 2 * g;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nnz; i += (int64_t)gridDim.x * blockDim.x) {
+    const int c = indices[i];
+    const double v = data[i];
+    atomicAdd(&mine[c], v);
+    atomicAdd(&mine[g + c], v * v);
+  }
+}
+__global__ void reduce_copies_f64_kernel(const double* __restrict__ src, int copies, int64_t len, double* __restrict__ dst) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= len) return;
+  double s = 0.0;
+  for (int c = 0; c < copies; ++c) s += src[(size_t)c * len + i];
+  dst[i] = s;
+}
+__global__ void reduce_copies_f32_to_f64_kernel(const float* __restrict__ src, int copies, int64_t len,
+                                                double* __restrict__ dst) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= len) return;
+  double s = 0.0;
+  for (int c = 0; c < copies; ++c) s += (double)src[(size_t)c * len + i];
+  dst[i] = s;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Y[r, 0:ncols_out] = sum_e data[e] * B[indices[e], :] - shift     (row stride of Y = ldy)
+template <int LPT>  // columns of B per lane: l = 32*LPT
+__global__ void __launch_bounds__(256)
+spmm_csr_kernel(int64_t n, const int64_t* __restrict__ indptr, const int32_t* __restrict__ indices,
+                const float* __restrict__ data, const float* __restrict__ B, const float* __restrict__ shift,
+                float* __restrict__ Y, int ldy, int ncols_out) {
+  constexpr int L = 32 * LPT;
+  const int lane = threadIdx.x & 31;
+  const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= n) return;
+  const int64_t e0 = indptr[row], e1 = indptr[row + 1];
+  float acc[LPT];
+#pragma unroll
+  for (int j = 0; j < LPT; ++j) acc[j] = 0.0f;
+  for (int64_t e = e0; e < e1; e += 32) {
+    const int cnt = (int)min((int64_t)32, e1 - e);
+    int c = 0;
+    float v = 0.0f;
+    if (lane < cnt) {
+      c = indices[e + lane];
+      v = data[e + lane];
+    }
+    for (int j = 0; j < cnt; ++j) {
+      const int cj = __shfl_sync(0xffffffffu, c, j);
+      const float vj = __shfl_sync(0xffffffffu, v, j);
+      const float* b = B + (size_t)cj * L + lane * LPT;
+      if (LPT == 1) {
+        acc[0] = fmaf(vj, b[0], acc[0]);
+      } else if (LPT == 2) {
+        const float2 bb = *reinterpret_cast<const float2*>(b);
+        acc[0] = fmaf(vj, bb.x, acc[0]);
+        acc[1] = fmaf(vj, bb.y, acc[1]);
+      } else {
+        const float4 bb = *reinterpret_cast<const float4*>(b);
+        acc[0] = fmaf(vj, bb.x, acc[0]);
+        acc[1] = fmaf(vj, bb.y, acc[1]);
+        acc[2] = fmaf(vj, bb.z, acc[2]);
+        acc[3] = fmaf(vj, bb.w, acc[3]);
+      }
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < LPT; ++j) {
+    const int col = lane * LPT + j;
+    if (col < ncols_out) Y[row * (int64_t)ldy + col] = acc[j] - (shift ? shift[col] : 0.0f);
+  }
+}
+
+// Z_copy[c, :] += data[e] * Y[r, :] for every non-zero (r, c); l in {32, 64, 128}
+template <int L>
+__global__ void __launch_bounds__(256)
+spmm_csr_t_kernel(int64_t n, const int64_t* __restrict__ indptr, const int32_t* __restrict__ indices,
+                  const float* __restrict__ data, const float* __restrict__ Y, float* __restrict__ Zc, int g) {
+  constexpr int LANES = L / 4;       // lanes per non-zero
+  constexpr int GROUPS = 32 / LANES;  // non-zeros per warp instruction
+  const int lane = threadIdx.x & 31;
+  const int sub = lane % LANES, grp = lane / LANES;
+  const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= n) return;
+  float* Z = Zc + (size_t)(blockIdx.x % ZT_COPIES) * g * L;
+  const float4 y = *reinterpret_cast<const float4*>(Y + row * (int64_t)L + 4 * sub);
+  const int64_t e0 = indptr[row], e1 = indptr[row + 1];
+  for (int64_t e = e0; e < e1; e += 32) {
+    const int cnt = (int)min((int64_t)32, e1 - e);
+    int c = 0;
+    float v = 0.0f;
+    if (lane < cnt) {
+      c = indices[e + lane];
+      v = data[e + lane];
+    }
+    for (int j = 0; j < cnt; j += GROUPS) {
+      const int jj = j + grp;
+      const int cj = __shfl_sync(0xffffffffu, c, jj & 31);
+      const float vj = __shfl_sync(0xffffffffu, v, jj & 31);
+      if (jj < cnt) {
+        float4* dst = reinterpret_cast<float4*>(Z + (size_t)cj * L + 4 * sub);
+        atomicAdd(dst, make_float4(vj * y.x, vj * y.y, vj * y.z, vj * y.w));
+      }
+    }
+  }
+}
+
+// G[ci, cj] += vi*vj for i <= j within a row (columns ascending within a CSR row => upper triangle
+// when the row is sorted; unsorted rows are handled by ordering the pair)
+__global__ void __launch_bounds__(256)
+csr_gram_kernel(int64_t n, const int64_t* __restrict__ indptr, const int32_t* __restrict__ indices,
+                const float* __restrict__ data, double* __restrict__ G, int g) {
+  const int lane = threadIdx.x & 31;
+  const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= n) return;
+  const int64_t e0 = indptr[row], e1 = indptr[row + 1];
+  for (int64_t i = e0; i < e1; ++i) {
+    const int ci = indices[i];
+    const double vi = data[i];
+    for (int64_t j = i + lane; j < e1; j += 32) {
+      const int cj = indices[j];
+      const double p = vi * (double)data[j];
+      const int a = min(ci, cj), b = max(ci, cj);
+      atomicAdd(&G[(size_t)a * g + b], p);
+    }
+  }
+}
+__global__ void mirror_upper_kernel(double* __restrict__ G, int g) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (int64_t)g * g) return;
+  const int r = (int)(i / g), c = (int)(i % g);
+  if (r > c) G[i] = G[(size_t)c * g + r];
+}
+// C = G - n * mu mu^T   (in place)
+__global__ void center_gram_kernel(double* __restrict__ G, const double* __restrict__ mu, double n_total, int g) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (int64_t)g * g) return;
+  const int r = (int)(i / g), c = (int)(i % g);
+  G[i] -= n_total * mu[r] * mu[c];
+}
+
+// ---------------------------------------------------------------------------------------------
+// small dense fp64 helpers on g x l blocks (row-major, leading dimension l)
+// S[l x l] += A^T B over a chunk of rows (grid.x chunks); S must be zeroed first
+__global__ void __launch_bounds__(256)
+tsmm_tn_kernel(const double* __restrict__ A, const double* __restrict__ B, int g, int l, double* __restrict__ S) {
+  extern __shared__ double sm[];  // [2][ROWS][l]
+  constexpr int ROWS = 32;
+  double* sa = sm;
+  double* sb = sm + ROWS * l;
+  const int r0 = blockIdx.x * ROWS;
+  const int rows = min(ROWS, g - r0);
+  for (int i = threadIdx.x; i < ROWS * l; i += blockDim.x) {
+    const int r = i / l;
+    sa[i] = r < rows ? A[(size_t)(r0 + r) * l + (i % l)] : 0.0;
+    sb[i] = r < rows ? B[(size_t)(r0 + r) * l + (i % l)] : 0.0;
+  }
+  __syncthreads();
+  for (int o = threadIdx.x; o < l * l; o += blockDim.x) {
+    const int i = o / l, j = o % l;
+    double s = 0.0;
+#pragma unroll 8
+    for (int r = 0; r < ROWS; ++r) s = fma(sa[r * l + i], sb[r * l + j], s);
+    atomicAdd(&S[o], s);
+  }
+}
+// C[g x lo] = A[g x l] * M[l x lo]
+__global__ void __launch_bounds__(256)
+right_mult_kernel(const double* __restrict__ A, const double* __restrict__ M, int g, int l, int lo,
+                  double* __restrict__ C) {
+  extern __shared__ double sm[];  // M
+  for (int i = threadIdx.x; i < l * lo; i += blockDim.x) sm[i] = M[i];
+  __syncthreads();
+  const int64_t o = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (o >= (int64_t)g * lo) return;
+  const int r = (int)(o / lo), c = (int)(o % lo);
+  double s = 0.0;
+  for (int k = 0; k < l; ++k) s = fma(A[(size_t)r * l + k], sm[k * lo + c], s);
+  C[o] = s;
+}
+// Z[g x l] = C[g x g] * V[g x l]   (C symmetric, dense fp64)
+__global__ void __launch_bounds__(256)
+dense_sym_apply_kernel(const double* __restrict__ C, const double* __restrict__ V, int g, int l, double* __restrict__ Z) {
+  constexpr int TR = 16, TK = 32;
+  extern __shared__ double sm[];  // Cs[TR][TK], Vs[TK][l]
+  double* Cs = sm;
+  double* Vs = sm + TR * TK;
+  const int r0 = blockIdx.x * TR;
+  // each thread owns outputs o = threadIdx.x + m*256 of the TR x l tile
+  double acc[8];
+#pragma unroll
+  for (int m = 0; m < 8; ++m) acc[m] = 0.0;
+  for (int k0 = 0; k0 < g; k0 += TK) {
+    for (int i = threadIdx.x; i < TR * TK; i += blockDim.x) {
+      const int r = i / TK, k = i % TK;
+      Cs[i] = (r0 + r < g && k0 + k < g) ? C[(size_t)(r0 + r) * g + k0 + k] : 0.0;
+    }
+    for (int i = threadIdx.x; i < TK * l; i += blockDim.x) {
+      const int k = i / l;
+      Vs[i] = (k0 + k < g) ? V[(size_t)(k0 + k) * l + (i % l)] : 0.0;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int m = 0; m < 8; ++m) {
+      const int o = threadIdx.x + m * 256;
+      if (o < TR * l) {
+        const int r = o / l, c = o % l;
+        double s = acc[m];
+#pragma unroll 8
+        for (int k = 0; k < TK; ++k) s = fma(Cs[r * TK + k], Vs[k * l + c], s);
+        acc[m] = s;
+      }
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int m = 0; m < 8; ++m) {
+    const int o = threadIdx.x + m * 256;
+    if (o < TR * l) {
+      const int r = o / l, c = o % l;
+      if (r0 + r < g) Z[(size_t)(r0 + r) * l + c] = acc[m];
+    }
+  }
+}
+// res2[j] += sum_r (Z[r,j] - theta[j] * V[r,j])^2 ; res2 zeroed first
+__global__ void residual_kernel(const double* __restrict__ Z, const double* __restrict__ V,
+                                const double* __restrict__ theta, int g, int l, double* __restrict__ res2) {
+  const int j = threadIdx.x % l;
+  const int rstep = blockDim.x / l;
+  double s = 0.0;
+  for (int r = blockIdx.x * rstep + threadIdx.x / l; r < g; r += gridDim.x * rstep) {
+    const double d = Z[(size_t)r * l + j] - theta[j] * V[(size_t)r * l + j];
+    s = fma(d, d, s);
+  }
+  if (threadIdx.x < rstep * l) atomicAdd(&res2[j], s);
+}
+__global__ void f64_to_f32_kernel(const double* __restrict__ s, float* __restrict__ d, int64_t n) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) d[i] = (float)s[i];
+}
+// components[k x g] (float32) = first k columns of U[g x l], transposed, times sign[j]
+__global__ void components_out_kernel(const double* __restrict__ U, const double* __restrict__ sign, int g, int l, int k,
+                                      float* __restrict__ comp) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (int64_t)k * g) return;
+  const int j = (int)(i / g), r = (int)(i % g);
+  comp[i] = (float)(U[(size_t)r * l + j] * sign[j]);
+}
+// per column j < l: value with max |.| (first occurrence); one block per column
+__global__ void col_absmax_kernel(const double* __restrict__ U, int g, int l, double* __restrict__ out) {
+  __shared__ double sv[256];
+  __shared__ int si[256];
+  const int j = blockIdx.x;
+  double best = -1.0;
+  int bi = 0x7fffffff;
+  for (int r = threadIdx.x; r < g; r += blockDim.x) {
+    const double a = fabs(U[(size_t)r * l + j]);
+    if (a > best) { best = a; bi = r; }
+  }
+  sv[threadIdx.x] = best;
+  si[threadIdx.x] = bi;
+  __syncthreads();
+  for (int s = blockDim.x / 2; s > 0; s >>= 1) {
+    if (threadIdx.x < s) {
+      const double o = sv[threadIdx.x + s];
+      const int oi = si[threadIdx.x + s];
+      if (o > sv[threadIdx.x] || (o == sv[threadIdx.x] && oi < si[threadIdx.x])) { sv[threadIdx.x] = o; si[threadIdx.x] = oi; }
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) out[j] = U[(size_t)si[0] * l + j];
+}
+
+// ---------------------------------------------------------------------------------------------
+// host fp64 small dense algebra
+// cyclic Jacobi: A (m x m symmetric, row-major, destroyed) -> eigenvalues w, eigenvectors V (columns)
+void jacobi_eigh(std::vector<double>& A, int m, std::vector<double>& w, std::vector<double>& V) {
+  V.assign((size_t)m * m, 0.0);
+  for (int i = 0; i < m; ++i) V[(size_t)i * m + i] = 1.0;
+  for (int sweep = 0; sweep < 60; ++sweep) {
+    double off = 0.0, diag = 0.0;
+    for (int i = 0; i < m; ++i) {
+      diag += A[(size_t)i * m + i] * A[(size_t)i * m + i];
+      for (int j = i + 1; j < m; ++j) off += A[(size_t)i * m + j] * A[(size_t)i * m + j];
+    }
+    if (off <= 1e-30 * (diag + off) || off == 0.0) break;
+    for (int p = 0; p < m - 1; ++p) {
+      for (int q = p + 1; q < m; ++q) {
+        const double apq = A[(size_t)p * m + q];
+        if (apq == 0.0) continue;
+        const double app = A[(size_t)p * m + p], aqq = A[(size_t)q * m + q];
+        if (fabs(apq) < 1e-300) continue;
+        const double tau = (aqq - app) / (2.0 * apq);
+        const double t = (tau >= 0.0 ? 1.0 : -1.0) / (fabs(tau) + sqrt(1.0 + tau * tau));
+        const double c = 1.0 / sqrt(1.0 + t * t), s = t * c;
+        for (int k = 0; k < m; ++k) {  // columns p,q
+          const double akp = A[(size_t)k * m + p], akq = A[(size_t)k * m + q];
+          A[(size_t)k * m + p] = c * akp - s * akq;
+          A[(size_t)k * m + q] = s * akp + c * akq;
+        }
+        for (int k = 0; k < m; ++k) {  // rows p,q
+          const double apk = A[(size_t)p * m + k], aqk = A[(size_t)q * m + k];
+          A[(size_t)p * m + k] = c * apk - s * aqk;
+          A[(size_t)q * m + k] = s * apk + c * aqk;
+        }
+        for (int k = 0; k < m; ++k) {
+          const double vkp = V[(size_t)k * m + p], vkq = V[(size_t)k * m + q];
+          V[(size_t)k * m + p] = c * vkp - s * vkq;
+          V[(size_t)k * m + q] = s * vkp + c * vkq;
+        }
+      }
+    }
+  }
+  w.resize(m);
+  for (int i = 0; i < m; ++i) w[i] = A[(size_t)i * m + i];
+}
+// sort eigenpairs descending
+void sort_desc(std::vector<double>& w, std::vector<double>& V, int m) {
+  std::vector<int> ord(m);
+  for (int i = 0; i < m; ++i) ord[i] = i;
+  std::stable_sort(ord.begin(), ord.end(), [&](int a, int b) { return w[a] > w[b]; });
+  std::vector<double> w2(m), V2((size_t)m * m);
+  for (int j = 0; j < m; ++j) {
+    w2[j] = w[ord[j]];
+    for (int i = 0; i < m; ++i) V2[(size_t)i * m + j] = V[(size_t)i * m + ord[j]];
+  }
+  w.swap(w2);
+  V.swap(V2);
+}
+// M = R^{-1} with S = R^T R (upper Cholesky); returns false if S is numerically rank deficient
+bool chol_inverse_upper(const std::vector<double>& S, int m, std::vector<double>& M) {
+  std::vector<double> R((size_t)m * m, 0.0);
+  double dmax = 0.0;
+  for (int i = 0; i < m; ++i) dmax = std::max(dmax, S[(size_t)i * m + i]);
+  for (int j = 0; j < m; ++j) {
+    double d = S[(size_t)j * m + j];
+    for (int k = 0; k < j; ++k) d -= R[(size_t)k * m + j] * R[(size_t)k * m + j];
+    if (!(d > 1e-11 * dmax)) return false;
+    const double rjj = sqrt(d);
+    R[(size_t)j * m + j] = rjj;
+    for (int i = j + 1; i < m; ++i) {
+      double s = S[(size_t)j * m + i];
+      for (int k = 0; k < j; ++k) s -= R[(size_t)k * m + j] * R[(size_t)k * m + i];
+      R[(size_t)j * m + i] = s / rjj;
+    }
+  }
+  M.assign((size_t)m * m, 0.0);  // upper-triangular inverse by back substitution
+  for (int j = 0; j < m; ++j) {
+    M[(size_t)j * m + j] = 1.0 / R[(size_t)j * m + j];
+    for (int i = j - 1; i >= 0; --i) {
+      double s = 0.0;
+      for (int k = i + 1; k <= j; ++k) s += R[(size_t)i * m + k] * M[(size_t)k * m + j];
+      M[(size_t)i * m + j] = -s / R[(size_t)i * m + i];
+    }
+  }
+  return true;
+}
+
+struct Rng {
+  uint64_t s;
+  explicit Rng(uint64_t seed) : s(seed * 0x9E3779B97F4A7C15ULL + 0xD1B54A32D192ED03ULL) {}
+  uint64_t next() {
+    uint64_t z = (s += 0x9E3779B97F4A7C15ULL);
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ULL;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL;
+    return z ^ (z >> 31);
+  }
+  double uniform() { return (double)(next() >> 11) * (1.0 / 9007199254740992.0); }
+  double normal() {
+    double u1 = uniform(), u2 = uniform();
+    if (u1 < 1e-300) u1 = 1e-300;
+    return sqrt(-2.0 * log(u1)) * cos(6.283185307179586 * u2);
+  }
+};
+
+struct PcaWork {
+  sb2_ctx* ctx;
+  cudaStream_t st;
+  int g, l;
+  // operator data
+  int solver;
+  int64_t n;
+  const int64_t* indptr;
+  const int32_t* indices;
+  const float* data;
+  double* d_mu;     // [g]
+  double* d_C;      // [g x g] (solver 1)
+  float* d_Bf;      // [g x l] fp32 copy of V
+  float* d_shift;   // [l]
+  float* d_Y;       // [n x l]
+  float* d_Zc;      // [ZT_COPIES x g x l]
+  double* d_S;      // [l x l]
+  double* d_M;      // [l x l]
+  double* d_tmp;    // [g x l]
+};
+
+int32_t launch_spmm(sb2_ctx* ctx, int64_t n, int l, const int64_t* indptr, const int32_t* indices, const float* data,
+                    const float* B, const float* shift, float* Y, int ldy, int ncols_out) {
+  const int wpb = 8;
+  const unsigned grid = (unsigned)ceil_div64(n, wpb);
+  if (n == 0) return SB2_OK;
+  if (l == 32) spmm_csr_kernel<1><<<grid, wpb * 32, 0, ctx->stream>>>(n, indptr, indices, data, B, shift, Y, ldy, ncols_out);
+  else if (l == 64) spmm_csr_kernel<2><<<grid, wpb * 32, 0, ctx->stream>>>(n, indptr, indices, data, B, shift, Y, ldy, ncols_out);
+  else if (l == 128) spmm_csr_kernel<4><<<grid, wpb * 32, 0, ctx->stream>>>(n, indptr, indices, data, B, shift, Y, ldy, ncols_out);
+  else { sb2_set_error("spmm: l must be 32, 64 or 128 (got %d)", l); return SB2_E_BADARG; }
+  SB2_LAUNCH_CHECK(ctx);
+  return SB2_OK;
+}
+int32_t launch_spmm_t(sb2_ctx* ctx, int64_t n, int g, int l, const int64_t* indptr, const int32_t* indices,
+                      const float* data, const float* Y, float* Zc, double* Z) {
+  const int wpb = 8;
+  const unsigned grid = (unsigned)ceil_div64(n, wpb);
+  SB2_CUDA(cudaMemsetAsync(Zc, 0, sizeof(float) * (size_t)ZT_COPIES * g * l, ctx->stream));
+  if (n > 0) {
+    if (l == 32) spmm_csr_t_kernel<32><<<grid, wpb * 32, 0, ctx->stream>>>(n, indptr, indices, data, Y, Zc, g);
+    else if (l == 64) spmm_csr_t_kernel<64><<<grid, wpb * 32, 0, ctx->stream>>>(n, indptr, indices, data, Y, Zc, g);
+    else if (l == 128) spmm_csr_t_kernel<128><<<grid, wpb * 32, 0, ctx->stream>>>(n, indptr, indices, data, Y, Zc, g);
+    else { sb2_set_error("spmm_t: l must be 32, 64 or 128 (got %d)", l); return SB2_E_BADARG; }
+    SB2_LAUNCH_CHECK(ctx);
+  }
+  const int64_t len = (int64_t)g * l;
+  reduce_copies_f32_to_f64_kernel<<<(unsigned)ceil_div64(len, 256), 256, 0, ctx->stream>>>(Zc, ZT_COPIES, len, Z);
+  SB2_LAUNCH_CHECK(ctx);
+  return SB2_OK;
+}
+
+// S = A^T B (device, l x l), copied to host
+int32_t tsmm_host(PcaWork& w, const double* A, const double* B, std::vector<double>& hS) {
+  const int l = w.l;
+  SB2_CUDA(cudaMemsetAsync(w.d_S, 0, sizeof(double) * l * l, w.st));
+  tsmm_tn_kernel<<<(unsigned)ceil_div64(w.g, 32), 256, sizeof(double) * 2 * 32 * l, w.st>>>(A, B, w.g, l, w.d_S);
+  SB2_LAUNCH_CHECK(w.ctx);
+  hS.resize((size_t)l * l);
+  SB2_CUDA(cudaMemcpyAsync(hS.data(), w.d_S, sizeof(double) * l * l, cudaMemcpyDeviceToHost, w.st));
+  SB2_CUDA(cudaStreamSynchronize(w.st));
+  return SB2_OK;
+}
+// A <- A * M (M host l x l)
+int32_t right_mult_inplace(PcaWork& w, double* A, const std::vector<double>& hM) {
+  const int l = w.l;
+  SB2_CUDA(cudaMemcpyAsync(w.d_M, hM.data(), sizeof(double) * l * l, cudaMemcpyHostToDevice, w.st));
+  right_mult_kernel<<<(unsigned)ceil_div64((int64_t)w.g * l, 256), 256, sizeof(double) * l * l, w.st>>>(A, w.d_M, w.g, l, l,
+                                                                                                  w.d_tmp);
+  SB2_LAUNCH_CHECK(w.ctx);
+  SB2_CUDA(cudaMemcpyAsync(A, w.d_tmp, sizeof(double) * (size_t)w.g * l, cudaMemcpyDeviceToDevice, w.st));
+  return SB2_OK;
+}
+// orthonormalise the columns of A (g x l): CholeskyQR, twice; eigen-based fallback if rank deficient
+int32_t orthonormalize(PcaWork& w, double* A) {
+  const int l = w.l;
+  std::vector<double> S, M;
+  for (int pass = 0; pass < 2; ++pass) {
+    SB2_TRY(tsmm_host(w, A, A, S));
+    if (!chol_inverse_upper(S, l, M)) {
+      std::vector<double> ev, W;
+      jacobi_eigh(S, l, ev, W);
+      double emax = 0.0;
+      for (double e : ev) emax = std::max(emax, e);
+      M.assign((size_t)l * l, 0.0);
+      for (int j = 0; j < l; ++j) {
+        const double sc = ev[j] > 1e-12 * emax ? 1.0 / sqrt(ev[j]) : 0.0;  // null directions -> zero columns
+        for (int i = 0; i < l; ++i) M[(size_t)i * l + j] = W[(size_t)i * l + j] * sc;
+      }
+    }
+    SB2_TRY(right_mult_inplace(w, A, M));
+  }
+  return SB2_OK;
+}
+__global__ void mu_dot_kernel(const double* __restrict__ mu, const double* __restrict__ V, int g, int l,
+                              float* __restrict__ shift) {
+  // one block per column j
+  __shared__ double red[256];
+  const int j = blockIdx.x;
+  double s = 0.0;
+  for (int r = threadIdx.x; r < g; r += blockDim.x) s = fma(mu[r], V[(size_t)r * l + j], s);
+  red[threadIdx.x] = s;
+  __syncthreads();
+  for (int k = blockDim.x / 2; k > 0; k >>= 1) {
+    if (threadIdx.x < k) red[threadIdx.x] += red[threadIdx.x + k];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) shift[j] = (float)red[0];
+}
+
+int32_t apply_operator_spmm(PcaWork& w, const double* V, double* Z) {
+  const int g = w.g, l = w.l;
+  const int64_t len = (int64_t)g * l;
+  f64_to_f32_kernel<<<(unsigned)ceil_div64(len, 256), 256, 0, w.st>>>(V, w.d_Bf, len);
+  SB2_LAUNCH_CHECK(w.ctx);
+  mu_dot_kernel<<<l, 256, 0, w.st>>>(w.d_mu, V, g, l, w.d_shift);
+  SB2_LAUNCH_CHECK(w.ctx);
+  SB2_TRY(launch_spmm(w.ctx, w.n, l, w.indptr, w.indices, w.data, w.d_Bf, w.d_shift, w.d_Y, l, l));
+  SB2_TRY(launch_spmm_t(w.ctx, w.n, g, l, w.indptr, w.indices, w.data, w.d_Y, w.d_Zc, Z));
+  SB2_TRY(sb2_comm_allreduce_f64(w.ctx, Z, len));
+  return SB2_OK;
+}
+
+// Z = A_op * V  (V, Z device g x l fp64); A_op = X_c^T X_c summed over all ranks
+int32_t apply_operator(PcaWork& w, const double* V, double* Z) {
+  if (w.solver == 1) {
+    dense_sym_apply_kernel<<<(unsigned)ceil_div64(w.g, 16), 256, sizeof(double) * (16 * 32 + 32 * w.l), w.st>>>(
+        w.d_C, V, w.g, w.l, Z);
+    SB2_LAUNCH_CHECK(w.ctx);
+    return SB2_OK;
+  }
+  return apply_operator_spmm(w, V, Z);
+}
+
+}  // namespace
+
+extern "C" {
+
+int32_t sb2_csr_col_stats(sb2_ctx* ctx, int64_t n, int32_t g, const int64_t* d_indptr, const int32_t* d_indices,
+                          const float* d_data, double* d_col_sum, double* d_col_sumsq) {
+  SB2_CHECK_ARG(ctx && d_indptr && d_col_sum && d_col_sumsq, "null pointer");
+  SB2_CHECK_ARG(n >= 0 && g >= 1, "shape");
+  SB2_CUDA(cudaSetDevice(ctx->device));
+  ScratchScope scr(ctx);
+  int64_t nnz = 0;
+  if (n > 0) {
+    SB2_CUDA(cudaMemcpyAsync(&nnz, d_indptr + n, sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->stream));
+    SB2_CUDA(cudaStreamSynchronize(ctx->stream));
+  }
+  double* acc;
+  SB2_TRY(scr.alloc(&acc, (size_t)STAT_COPIES * 2 * g));
+  SB2_CUDA(cudaMemsetAsync(acc, 0, sizeof(double) * STAT_COPIES * 2 * g, ctx->stream));
+  if (nnz > 0) {
+    const int grid = ctx->prop.multiProcessorCount * 8;
+    csr_col_stats_kernel<<<grid, 256, 0, ctx->stream>>>(nnz, d_indices, d_data, g, acc);
+    SB2_LAUNCH_CHECK(ctx);
+  }
+  double* both;
+  SB2_TRY(scr.alloc(&both, (size_t)2 * g));
+  reduce_copies_f64_kernel<<<(unsigned)ceil_div64(2 * g, 256), 256, 0, ctx->stream>>>(acc, STAT_COPIES, 2 * (int64_t)g, both);
+  SB2_LAUNCH_CHECK(ctx);
+  SB2_CUDA(cudaMemcpyAsync(d_col_sum, both, sizeof(double) * g, cudaMemcpyDeviceToDevice, ctx->stream));
+  SB2_CUDA(cudaMemcpyAsync(d_col_sumsq, both + g, sizeof(double) * g, cudaMemcpyDeviceToDevice, ctx->stream));
+  return SB2_OK;
+}
+
+int32_t sb2_spmm_csr(sb2_ctx* ctx, int64_t n, int32_t g, int32_t l, const int64_t* d_indptr, const int32_t* d_indices,
+                     const float* d_data, const float* d_b, const float* d_shift, float* d_y) {
+  SB2_CHECK_ARG(ctx && d_indptr && d_b && d_y, "null pointer");
+  (void)g;
+  SB2_CUDA(cudaSetDevice(ctx->device));
+  return launch_spmm(ctx, n, l, d_indptr, d_indices, d_data, d_b, d_shift, d_y, l, l);
+}
+
+int32_t sb2_spmm_csr_t(sb2_ctx* ctx, int64_t n, int32_t g, int32_t l, const int64_t* d_indptr,
+                       const int32_t* d_indices, const float* d_data, const float* d_y, double* d_z) {
+  SB2_CHECK_ARG(ctx && d_indptr && d_y && d_z, "null pointer");
+  SB2_CUDA(cudaSetDevice(ctx->device));
+  ScratchScope scr(ctx);
+  float* Zc;
+  SB2_TRY(scr.alloc(&Zc, (size_t)ZT_COPIES * g * l));
+  return launch_spmm_t(ctx, n, g, l, d_indptr, d_indices, d_data, d_y, Zc, d_z);
+}
+
+int32_t sb2_csr_gram(sb2_ctx* ctx, int64_t n, int32_t g, const int64_t* d_indptr, const int32_t* d_indices,
+                     const float* d_data, double* d_gram) {
+  SB2_CHECK_ARG(ctx && d_indptr && d_gram, "null pointer");
+  SB2_CUDA(cudaSetDevice(ctx->device));
+  SB2_CUDA(cudaMemsetAsync(d_gram, 0, sizeof(double) * (size_t)g * g, ctx->stream));
+  if (n > 0) {
+    csr_gram_kernel<<<(unsigned)ceil_div64(n, 8), 256, 0, ctx->stream>>>(n, d_indptr, d_indices, d_data, d_gram, g);
+    SB2_LAUNCH_CHECK(ctx);
+  }
+  mirror_upper_kernel<<<(unsigned)ceil_div64((int64_t)g * g, 256), 256, 0, ctx->stream>>>(d_gram, g);
+  SB2_LAUNCH_CHECK(ctx);
+  return SB2_OK;
+}
+
+int32_t sb2_pca_csr_f32(sb2_ctx* ctx, int64_t n, int64_t n_total, int32_t g, const int64_t* d_indptr,
+                        const int32_t* d_indices, const float* d_data, int32_t k, int32_t solver, int32_t max_iter,
+                        double tol, uint64_t seed, float* d_x_pca, float* d_components, double* h_var,
+                        double* h_var_ratio, double* h_mean, sb2_pca_info* info) {
+  SB2_CHECK_ARG(ctx && d_indptr && d_x_pca && d_components && h_var && h_var_ratio && h_mean, "null pointer");
+  SB2_CHECK_ARG(n >= 0 && n_total >= n && n_total >= 2 && g >= 1, "shape");
+  SB2_CHECK_ARG(k >= 1 && k < std::min<int64_t>(n_total, g), "n_components must be between 1 and min(n_samples, n_features)-1");
+  SB2_CHECK_ARG(k <= 120, "n_components <= 120");
+  SB2_CHECK_ARG(solver == 0 || solver == 1, "solver");
+  SB2_CUDA(cudaSetDevice(ctx->device));
+  cudaStream_t st = ctx->stream;
+  ScratchScope scr(ctx);
+  // block width: k + oversampling, one of the kernel-supported widths
+  const int l = (k + 8 <= 32) ? 32 : (k + 8 <= 64 ? 64 : 128);
+  // tiny feature spaces: the block cannot be wider than g; the dense Gram route handles them
+  if (g < l) solver = 1;
+  if (max_iter <= 0) max_iter = solver == 1 ? 4000 : 300;
+  if (!(tol > 0.0)) tol = solver == 1 ? 1e-10 : 2e-6;
+
+  PcaWork w{};
+  w.ctx = ctx; w.st = st; w.g = g; w.l = l; w.solver = solver; w.n = n;
+  w.indptr = d_indptr; w.indices = d_indices; w.data = d_data;
+
+  // ---- column statistics -> mean, total variance ----
+  double *d_sum, *d_sumsq;
+  SB2_TRY(scr.alloc(&d_sum, (size_t)2 * g));
+  d_sumsq = d_sum + g;
+  SB2_TRY(sb2_csr_col_stats(ctx, n, g, d_indptr, d_indices, d_data, d_sum, d_sumsq));
+  SB2_TRY(sb2_comm_allreduce_f64(ctx, d_sum, 2 * (int64_t)g));
+  std::vector<double> hs(2 * (size_t)g);
+  SB2_CUDA(cudaMemcpyAsync(hs.data(), d_sum, sizeof(double) * 2 * g, cudaMemcpyDeviceToHost, st));
+  SB2_CUDA(cudaStreamSynchronize(st));
+  double total_var = 0.0;
+  const double nt = (double)n_total;
+  for (int j = 0; j < g; ++j) {
+    const double mu = hs[j] / nt;
+    h_mean[j] = mu;
+    total_var += (hs[g + j] - nt * mu * mu) / (nt - 1.0);  // per-gene variance, ddof=1 (_pca.py:727-729)
+  }
+  SB2_TRY(scr.alloc(&w.d_mu, (size_t)g));
+  SB2_CUDA(cudaMemcpyAsync(w.d_mu, h_mean, sizeof(double) * g, cudaMemcpyHostToDevice, st));
+
+  const int gl = (g < l) ? g : l;  // effective block width for tiny g handled below
+  (void)gl;
+
+  // ---- operator setup ----
+  SB2_TRY(scr.alloc(&w.d_S, (size_t)l * l));
+  SB2_TRY(scr.alloc(&w.d_M, (size_t)l * l));
+  double *d_V, *d_Z, *d_theta, *d_res;
+  const int gp = std::max(g, l);  // pad tiny feature spaces with all-zero genes (eigenvalue 0)
+  w.g = gp;
+  SB2_TRY(scr.alloc(&d_V, (size_t)gp * l));
+  SB2_TRY(scr.alloc(&d_Z, (size_t)gp * l));
+  SB2_TRY(scr.alloc(&w.d_tmp, (size_t)gp * l));
+  SB2_TRY(scr.alloc(&d_theta, (size_t)l));
+  SB2_TRY(scr.alloc(&d_res, (size_t)l));
+  SB2_TRY(scr.alloc(&w.d_Bf, (size_t)gp * l));
+  if (solver == 1) {
+    SB2_TRY(scr.alloc(&w.d_C, (size_t)gp * gp));
+    if (gp == g) {
+      SB2_TRY(sb2_csr_gram(ctx, n, g, d_indptr, d_indices, d_data, w.d_C));
+    } else {
+      double* Gs;
+      SB2_TRY(scr.alloc(&Gs, (size_t)g * g));
+      SB2_TRY(sb2_csr_gram(ctx, n, g, d_indptr, d_indices, d_data, Gs));
+      SB2_CUDA(cudaMemsetAsync(w.d_C, 0, sizeof(double) * (size_t)gp * gp, st));
+      SB2_CUDA(cudaMemcpy2DAsync(w.d_C, sizeof(double) * gp, Gs, sizeof(double) * g, sizeof(double) * g, g,
+                                 cudaMemcpyDeviceToDevice, st));
+    }
+    SB2_TRY(sb2_comm_allreduce_f64(ctx, w.d_C, (int64_t)gp * gp));
+    if (gp != g) {  // mu padded with zeros
+      double* mup;
+      SB2_TRY(scr.alloc(&mup, (size_t)gp));
+      SB2_CUDA(cudaMemsetAsync(mup, 0, sizeof(double) * gp, st));
+      SB2_CUDA(cudaMemcpyAsync(mup, w.d_mu, sizeof(double) * g, cudaMemcpyDeviceToDevice, st));
+      w.d_mu = mup;
+    }
+    center_gram_kernel<<<(unsigned)ceil_div64((int64_t)gp * gp, 256), 256, 0, st>>>(w.d_C, w.d_mu, nt, gp);
+    SB2_LAUNCH_CHECK(ctx);
+    SB2_CUDA(cudaFuncSetAttribute(dense_sym_apply_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)(sizeof(double) * (16 * 32 + 32 * l))));
+  } else {
+    SB2_TRY(scr.alloc(&w.d_shift, (size_t)l));
+    SB2_TRY(scr.alloc(&w.d_Y, (size_t)std::max<int64_t>(n, 1) * l));
+    SB2_TRY(scr.alloc(&w.d_Zc, (size_t)ZT_COPIES * g * l));
+  }
+  SB2_CUDA(cudaFuncSetAttribute(tsmm_tn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(double) * 2 * 32 * l)));
+  SB2_CUDA(cudaFuncSetAttribute(right_mult_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(double) * l * l)));
+
+  // ---- start block (identical on every rank: same seed) ----
+  {
+    std::vector<double> hv((size_t)gp * l, 0.0);
+    Rng rng(seed);
+    for (int r = 0; r < g; ++r)
+      for (int j = 0; j < l; ++j) hv[(size_t)r * l + j] = rng.normal();
+    SB2_CUDA(cudaMemcpyAsync(d_V, hv.data(), sizeof(double) * (size_t)gp * l, cudaMemcpyHostToDevice, st));
+    SB2_CUDA(cudaStreamSynchronize(st));
+  }
+  SB2_TRY(orthonormalize(w, d_V));
+
+  // ---- block subspace iteration with Rayleigh-Ritz ----
+  std::vector<double> T, theta, W, hres(l);
+  int it = 0, converged = 0;
+  double max_rel = 1e300, prev_rel = 1e300;
+  int stalled = 0;
+  const int check_every = solver == 1 ? 8 : 4;
+  for (;;) {
+    SB2_TRY(apply_operator(w, d_V, d_Z));
+    ++it;
+    const bool check = (it % check_every == 0) || it >= max_iter || it <= 1;
+    if (check) {
+      SB2_TRY(tsmm_host(w, d_V, d_Z, T));
+      for (int i = 0; i < l; ++i)  // symmetrise
+        for (int j = i + 1; j < l; ++j) {
+          const double a = 0.5 * (T[(size_t)i * l + j] + T[(size_t)j * l + i]);
+          T[(size_t)i * l + j] = T[(size_t)j * l + i] = a;
+        }
+      jacobi_eigh(T, l, theta, W);
+      sort_desc(theta, W, l);
+      SB2_TRY(right_mult_inplace(w, d_V, W));  // V <- Ritz vectors
+      SB2_TRY(right_mult_inplace(w, d_Z, W));  // Z <- A * Ritz vectors
+      SB2_CUDA(cudaMemcpyAsync(d_theta, theta.data(), sizeof(double) * l, cudaMemcpyHostToDevice, st));
+      SB2_CUDA(cudaMemsetAsync(d_res, 0, sizeof(double) * l, st));
+      {
+        const int threads = (1024 / l) * l;
+        residual_kernel<<<32, threads, 0, st>>>(d_Z, d_V, d_theta, gp, l, d_res);
+        SB2_LAUNCH_CHECK(ctx);
+      }
+      SB2_CUDA(cudaMemcpyAsync(hres.data(), d_res, sizeof(double) * l, cudaMemcpyDeviceToHost, st));
+      SB2_CUDA(cudaStreamSynchronize(st));
+      max_rel = 0.0;
+      const double th1 = std::max(theta[0], 1e-300);
+      for (int j = 0; j < k; ++j) max_rel = std::max(max_rel, sqrt(std::max(hres[j], 0.0)) / th1);
+      if (max_rel <= tol) { converged = 1; break; }
+      if (it >= max_iter) break;
+      // stagnation at the operator's rounding floor (fp32 SpMM passes): stop, report not converged
+      if (it > 1 && max_rel > 0.97 * prev_rel) { if (++stalled >= 3) break; } else stalled = 0;
+      prev_rel = max_rel;
+    }
+    // next block: V <- orth(Z)
+    SB2_CUDA(cudaMemcpyAsync(d_V, d_Z, sizeof(double) * (size_t)gp * l, cudaMemcpyDeviceToDevice, st));
+    SB2_TRY(orthonormalize(w, d_V));
+  }
+  // d_V now holds Ritz vectors (columns, descending theta)
+
+  // ---- sign convention: svd_flip(u_based_decision=False) (sklearn/utils/extmath.py:974-981) ----
+  std::vector<double> hsign(l, 1.0);
+  {
+    double* d_am;
+    SB2_TRY(scr.alloc(&d_am, (size_t)l));
+    col_absmax_kernel<<<l, 256, 0, st>>>(d_V, gp, l, d_am);
+    SB2_LAUNCH_CHECK(ctx);
+    std::vector<double> am(l);
+    SB2_CUDA(cudaMemcpyAsync(am.data(), d_am, sizeof(double) * l, cudaMemcpyDeviceToHost, st));
+    SB2_CUDA(cudaStreamSynchronize(st));
+    for (int j = 0; j < l; ++j) hsign[j] = am[j] < 0.0 ? -1.0 : 1.0;
+    SB2_CUDA(cudaMemcpyAsync(d_am, hsign.data(), sizeof(double) * l, cudaMemcpyHostToDevice, st));
+    // components_ = Vt (k x g)
+    // (rows beyond g in the padded space are all-zero genes and are dropped)
+    {
+      // compact U (gp x l) -> first g rows are contiguous already (row-major, ld = l)
+      components_out_kernel<<<(unsigned)ceil_div64((int64_t)k * g, 256), 256, 0, st>>>(d_V, d_am, g, l, k, d_components);
+      SB2_LAUNCH_CHECK(ctx);
+    }
+    // ---- X_pca = X * U - 1 * (mu^T U), U = sign-fixed Ritz vectors ----
+    // scale columns by sign, convert to fp32 (g x l), project with the SpMM kernel
+    std::vector<double> Dg((size_t)l * l, 0.0);
+    for (int j = 0; j < l; ++j) Dg[(size_t)j * l + j] = hsign[j];
+    SB2_TRY(right_mult_inplace(w, d_V, Dg));
+    const int64_t len = (int64_t)g * l;
+    f64_to_f32_kernel<<<(unsigned)ceil_div64(len, 256), 256, 0, st>>>(d_V, w.d_Bf, len);
+    SB2_LAUNCH_CHECK(ctx);
+    float* d_shift;
+    SB2_TRY(scr.alloc(&d_shift, (size_t)l));
+    mu_dot_kernel<<<l, 256, 0, st>>>(w.d_mu, d_V, g, l, d_shift);
+    SB2_LAUNCH_CHECK(ctx);
+    SB2_TRY(launch_spmm(ctx, n, l, d_indptr, d_indices, d_data, w.d_Bf, d_shift, d_x_pca, k, k));
+  }
+  for (int j = 0; j < k; ++j) {
+    const double ev = std::max(theta[j], 0.0) / (nt - 1.0);  // explained_variance_ = S^2/(n-1) (_pca.py:760-779)
+    h_var[j] = ev;
+    h_var_ratio[j] = total_var > 0.0 ? ev / total_var : 0.0;
+  }
+  SB2_CUDA(cudaStreamSynchronize(st));
+  if (info) {
+    info->iterations = it;
+    info->converged = converged;
+    info->max_rel_residual = max_rel;
+    info->total_var = total_var;
+  }
+  return SB2_OK;
+}
+
+}  // extern "C"
