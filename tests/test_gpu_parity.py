@@ -1,0 +1,284 @@
+"""GPU parity tests (run on the B200 box: `pytest -m gpu`).  Every product call goes through the C ABI
+(ctypes -> libscanpy_b200.so); the oracle (tests-only) is the checker.
+
+Bars (BASELINE.json north_star): X_pca within 1e-4 relative up to sign, identical kNN index sets,
+Leiden ARI >= 0.99 (on unambiguous, planted partitions).
+"""
+import numpy as np
+import pytest
+from scipy import sparse
+from sklearn.metrics import adjusted_rand_score
+
+import scanpy_b200 as sb
+from oracle import fuzzy as ofz, knn as oknn, leiden as old, pca as opca
+from scanpy_b200 import _ops
+from scanpy_b200._synth import synth_scipy
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def synth_small():
+    x, lab = synth_scipy(6000, 800, n_clusters=12, r=48)
+    return x, lab
+
+
+def _rel_err(a, b):
+    a = opca.align_signs(np.asarray(a, np.float64), b)
+    return np.linalg.norm(a - b, axis=0) / np.linalg.norm(b, axis=0)
+
+
+# ------------------------------------------------------------------------------------------ PCA
+@pytest.mark.parametrize("solver", ["arpack", "covariance_eigh", "b200_spmm"])
+def test_pca_golden_A_pca(literals, solver):
+    # reference golden: tests/test_pca.py:34-59,225-233 (norm(|A_pca[:, :4]| - |X_pca|) < 2e-5)
+    a = sparse.csr_matrix(literals["A_list"].astype(np.float32))
+    x_pca = sb.pp.pca(a, n_comps=4, svd_solver=solver)
+    assert x_pca.dtype == np.float32
+    assert np.linalg.norm(np.abs(literals["A_pca"][:, :4]) - np.abs(x_pca)) < 2e-5
+    # dense input gives the same (tests/test_pca.py:62-80 array-type matrix)
+    x_dense = sb.pp.pca(literals["A_list"].astype(np.float32), n_comps=4, svd_solver=solver)
+    np.testing.assert_allclose(np.abs(x_dense), np.abs(x_pca), atol=2e-5)
+
+
+@pytest.mark.parametrize("solver,tol", [(1, 1e-4), (0, 1e-4)])
+def test_pca_matches_reference(synth_small, solver, tol):
+    x, _ = synth_small
+    k = 30
+    out = _ops.pca_csr(x, k, solver=solver)
+    ref32 = opca.pca_arpack(x, k)                                       # the reference call, float32 ARPACK
+    ref64 = opca.pca_arpack(x.astype(np.float64), k, dtype="float64")   # same call in double = ground truth
+    s = ref64["singular_values"]
+    gap = np.r_[s[:-1] - s[1:], s[-1] * 1e-3] / s
+    e64 = _rel_err(out["X_pca"], ref64["X_pca"])
+    noise = _rel_err(ref32["X_pca"], ref64["X_pca"])  # the reference's own float32 noise per component
+    # 1e-4 relative (up to sign) on every component against ground truth ...
+    assert e64.max() < tol, (e64.max(), gap.min())
+    # ... and against the float32 reference within its own noise
+    e32 = _rel_err(out["X_pca"], ref32["X_pca"].astype(np.float64))
+    assert (e32 < np.maximum(1e-4, 2.0 * noise + 1e-5)).all(), (e32.max(), noise.max())
+    np.testing.assert_allclose(out["variance"], ref64["variance"], rtol=1e-5)
+    np.testing.assert_allclose(out["variance_ratio"], ref64["variance_ratio"], rtol=1e-5)
+    np.testing.assert_allclose(out["mean"], ref64["mean"], rtol=1e-6, atol=1e-9)
+    # sign convention svd_flip(u_based_decision=False): max-|.| entry of each component positive
+    comp = out["components"]
+    assert (comp[np.arange(k), np.abs(comp).argmax(axis=1)] > 0).all()
+    np.testing.assert_allclose(np.abs(comp), np.abs(ref64["components"]), atol=2e-4)
+    # components orthonormal, X_pca columns uncorrelated (tests/test_pca.py style invariants)
+    np.testing.assert_allclose(comp @ comp.T, np.eye(k), atol=1e-5)
+
+
+def test_pca_anndata_writeback_and_mask(synth_small):
+    x, _ = synth_small
+    x = x[:1500]
+    ad = sb.MiniAnnData(x)
+    rs = np.random.RandomState(1)
+    mask = rs.rand(x.shape[1]) < 0.6
+    ad.var["highly_variable"] = mask
+    sb.pp.pca(ad, n_comps=10)  # mask_var defaults to var['highly_variable'] (_pca/__init__.py:221-232)
+    assert ad.obsm["X_pca"].shape == (1500, 10) and ad.obsm["X_pca"].dtype == np.float32
+    assert ad.varm["PCs"].shape == (x.shape[1], 10)
+    assert (ad.varm["PCs"][~mask] == 0).all() and np.abs(ad.varm["PCs"][mask]).sum() > 0
+    assert ad.uns["pca"]["params"] == dict(zero_center=True, mask_var="highly_variable")
+    assert ad.uns["pca"]["variance"].shape == (10,) and ad.uns["pca"]["variance_ratio"].shape == (10,)
+    # mask == explicit subset (tests/test_pca.py:461-506)
+    sub = sb.pp.pca(x[:, mask], n_comps=10)
+    np.testing.assert_allclose(np.abs(sub), np.abs(ad.obsm["X_pca"]), atol=2e-4)
+    # same seed -> identical, copy=True leaves the input untouched (tests/test_pca.py:333-354)
+    ad2 = sb.pp.pca(sb.MiniAnnData(x), n_comps=10, copy=True)
+    ad3 = sb.pp.pca(sb.MiniAnnData(x), n_comps=10, copy=True, random_state=0)
+    np.testing.assert_array_equal(ad2.obsm["X_pca"], ad3.obsm["X_pca"])
+    # n_comps default = min(50, min(shape)-1) (tests/test_pca.py:277-290)
+    tiny = sb.pp.pca(x[:20, :30], return_info=True)
+    assert tiny[0].shape == (20, 19) and tiny[1].shape == (19, 30)
+
+
+def test_pca_building_blocks_linear_algebra(synth_small):
+    # size-independent properties: SpMM linearity, X^T(XB) == G B, column stats == numpy
+    import torch
+
+    x, _ = synth_small
+    n, g = x.shape
+    ctx = sb._abi.default_context()
+    dp, di, dd = _ops.csr_to_device(x)
+    rs = np.random.RandomState(0)
+    b = rs.standard_normal((g, 64)).astype(np.float32)
+    d_b = torch.from_numpy(b).cuda()
+    y = torch.empty((n, 64), dtype=torch.float32, device="cuda")
+    sb._abi.check(ctx.lib.sb2_spmm_csr(ctx.handle, n, g, 64, _ops.ptr(dp), _ops.ptr(di), _ops.ptr(dd), _ops.ptr(d_b), None, _ops.ptr(y)))
+    y_ref = x.astype(np.float64) @ b.astype(np.float64)
+    np.testing.assert_allclose(y.cpu().numpy(), y_ref, rtol=2e-5, atol=2e-5)
+    z = torch.empty((g, 64), dtype=torch.float64, device="cuda")
+    sb._abi.check(ctx.lib.sb2_spmm_csr_t(ctx.handle, n, g, 64, _ops.ptr(dp), _ops.ptr(di), _ops.ptr(dd), _ops.ptr(y), _ops.ptr(z)))
+    z_ref = x.astype(np.float64).T @ y.cpu().numpy().astype(np.float64)
+    np.testing.assert_allclose(z.cpu().numpy(), z_ref, rtol=2e-4, atol=2e-3 * np.abs(z_ref).max() * 1e-2)
+    gram = torch.empty((g, g), dtype=torch.float64, device="cuda")
+    sb._abi.check(ctx.lib.sb2_csr_gram(ctx.handle, n, g, _ops.ptr(dp), _ops.ptr(di), _ops.ptr(dd), _ops.ptr(gram)))
+    g_ref = (x.astype(np.float64).T @ x.astype(np.float64)).toarray()
+    np.testing.assert_allclose(gram.cpu().numpy(), g_ref, rtol=1e-12, atol=1e-9)
+    s1 = torch.empty(g, dtype=torch.float64, device="cuda"); s2 = torch.empty(g, dtype=torch.float64, device="cuda")
+    sb._abi.check(ctx.lib.sb2_csr_col_stats(ctx.handle, n, g, _ops.ptr(dp), _ops.ptr(di), _ops.ptr(dd), _ops.ptr(s1), _ops.ptr(s2)))
+    xd = x.astype(np.float64)
+    np.testing.assert_allclose(s1.cpu().numpy(), np.asarray(xd.sum(axis=0)).ravel(), rtol=1e-12)
+    np.testing.assert_allclose(s2.cpu().numpy(), np.asarray(xd.multiply(xd).sum(axis=0)).ravel(), rtol=1e-12)
+
+
+# ------------------------------------------------------------------------------------------ kNN
+def test_knn_golden_4points(literals):
+    # tests/test_neighbors.py:23-39,151-192
+    x, k = literals["X4"].astype(np.float32), int(literals["n_neighbors4"])
+    idx, dist, _ = _ops.knn(x, k)
+    assert (idx[:, 0] == np.arange(4)).all()
+    d = sb.pp._get_sparse_matrix_from_indices_distances(idx, dist, keep_self=False).toarray()
+    np.testing.assert_allclose(d, literals["distances_euclidean"], rtol=1e-6)
+
+
+def test_knn_golden_pbmc68k(pbmc68k_graph):
+    f = pbmc68k_graph
+    k = int(f["n_neighbors"][0])
+    idx, dist, _ = _ops.knn(np.ascontiguousarray(f["X_pca"][:, :30]), k)
+    for i in range(700):
+        assert set(f["dist_indices"][f["dist_indptr"][i]:f["dist_indptr"][i + 1]].tolist()) == set(idx[i, 1:].tolist())
+    np.testing.assert_allclose(dist[:, 1:], np.sort(f["dist_data"].reshape(700, k - 1), axis=1), rtol=1e-5)
+
+
+@pytest.mark.parametrize("n,d,k", [(1, 3, 1), (5, 2, 5), (127, 7, 15), (129, 50, 15), (1000, 50, 30), (4097, 33, 10),
+                                   (12345, 50, 15), (3000, 100, 30), (2000, 200, 8)])
+def test_knn_identical_index_sets(n, d, k):
+    rs = np.random.RandomState(n + d)
+    x = rs.standard_normal((n, d)).astype(np.float32)
+    x[: n // 3] += 2.5  # two blobs
+    idx, dist, info = _ops.knn(x, k)
+    oi, od = oknn.knn_brute(x, k) if n > 1 else (np.zeros((1, 1), int), np.zeros((1, 1)))
+    assert idx.shape == (n, k) and idx.dtype == np.int32 and dist.dtype == np.float64
+    assert (idx[:, 0] == np.arange(n)).all() and (dist[:, 0] == 0).all()
+    assert (np.diff(dist, axis=1) >= 0).all()  # ascending rows
+    assert oknn.same_neighbor_sets(idx, dist, oi, od).all()
+    np.testing.assert_allclose(dist, od, rtol=1e-6, atol=1e-7)
+
+
+def test_knn_duplicates_zero_rows_and_scale():
+    rs = np.random.RandomState(3)
+    x = np.zeros((600, 12), np.float32)          # 200 all-zero cells (legal: empty CSR rows) -> exact ties
+    x[200:] = rs.standard_normal((400, 12))
+    x[300:340] = x[299]                          # a block of exact duplicates
+    idx, dist, info = _ops.knn(x, 15)
+    oi, od = oknn.knn_brute(x, 15)
+    np.testing.assert_allclose(dist, od, atol=1e-6)          # distances identical even where ids tie
+    assert (idx[:, 0] == np.arange(600)).all()               # self forced into column 0
+    assert info["n_uncertified"] >= 240                      # tie rows went through the exact fallback
+    assert oknn.same_neighbor_sets(idx, dist, oi, od, rtol=1e-9).all()
+    # far-from-origin data: rounding bound grows, certificate must still give exact sets
+    y = rs.standard_normal((3000, 20)).astype(np.float32) * 0.01 + 1000.0
+    idx, dist, info = _ops.knn(y, 10)
+    oi, od = oknn.knn_brute(y, 10)
+    assert oknn.same_neighbor_sets(idx, dist, oi, od).all()
+
+
+def test_knn_transformer_in_reference_pipeline_shape():
+    # KnnTransformerLike contract (src/scanpy/neighbors/_types.py:53-64, _common.py:126-143)
+    rs = np.random.RandomState(0)
+    x = rs.standard_normal((500, 20)).astype(np.float32)
+    t = sb.B200KNNTransformer(n_neighbors=15)
+    d = t.fit_transform(x)
+    assert sparse.issparse(d) and d.shape == (500, 500) and (d.getnnz(axis=1) == 15).all()
+    i, dist = oknn.indices_distances_from_sparse(d, 15)  # the reference's own post-processing
+    oi, od = oknn.knn_brute(x, 15)
+    assert oknn.same_neighbor_sets(i, dist, oi, od).all()
+
+
+# ------------------------------------------------------------------------------------------ connectivities
+def test_fuzzy_goldens(literals, pbmc68k_graph):
+    x, k = literals["X4"].astype(np.float32), int(literals["n_neighbors4"])
+    idx, dist, _ = _ops.knn(x, k)
+    c, _, _ = _ops.fuzzy_simplicial_set(idx, dist)
+    np.testing.assert_allclose(c.toarray(), literals["connectivities_umap"], atol=5e-8)  # tests/test_neighbors.py:43-48
+    f = pbmc68k_graph
+    n, k = 700, int(f["n_neighbors"][0])
+    di, dd = f["dist_indices"].reshape(n, k - 1), f["dist_data"].reshape(n, k - 1)
+    o = np.argsort(dd, axis=1, kind="stable")
+    idx = np.hstack([np.arange(n)[:, None], np.take_along_axis(di, o, 1)]).astype(np.int32)
+    dist = np.hstack([np.zeros((n, 1)), np.take_along_axis(dd, o, 1)])
+    c, _, _ = _ops.fuzzy_simplicial_set(idx, dist)
+    g = sparse.csr_matrix((f["conn_data"], f["conn_indices"], f["conn_indptr"]), shape=(n, n))
+    g.sort_indices()
+    assert c.nnz == 9992 and (c.indices == g.indices).all() and (c.indptr == g.indptr).all()
+    np.testing.assert_allclose(c.data, g.data, atol=5e-7)
+
+
+@pytest.mark.parametrize("n,k", [(50, 5), (3000, 15), (20000, 30)])
+def test_fuzzy_matches_oracle(n, k):
+    rs = np.random.RandomState(n)
+    x = rs.standard_normal((n, 10)).astype(np.float32)
+    x[: n // 10] = x[0]  # duplicates -> zero distances -> rho / sigma-floor branches
+    idx, dist, _ = _ops.knn(x, k)
+    c, sig, rho = _ops.fuzzy_simplicial_set(idx, dist)
+    oc, osig, orho = ofz.fuzzy_simplicial_set(idx, dist, n, k)
+    assert c.dtype == np.float32 and c.has_sorted_indices and (c.data != 0).all() and c.diagonal().sum() == 0
+    assert abs(c - c.T).max() == 0  # exactly symmetric
+    oc.sort_indices()
+    assert c.nnz == oc.nnz and (c.indices == oc.indices).all()
+    np.testing.assert_allclose(c.data, oc.data, rtol=2e-6, atol=1e-7)
+    np.testing.assert_allclose(rho, orho, rtol=0, atol=0)
+    np.testing.assert_allclose(sig, osig, rtol=1e-6)
+
+
+# ------------------------------------------------------------------------------------------ Leiden
+def test_leiden_properties_and_quality(pbmc68k_graph):
+    f = pbmc68k_graph
+    n = 700
+    g = sparse.csr_matrix((f["conn_data"].astype(np.float32), f["conn_indices"], f["conn_indptr"]), shape=(n, n))
+    m0, q0, info = _ops.leiden(g, seed=0)
+    m0b, q0b, _ = _ops.leiden(g, seed=0)
+    assert (m0 == m0b).all() and q0 == q0b                 # same seed -> identical (tests/test_clustering.py:67-102)
+    m1, _, _ = _ops.leiden(g, seed=1)
+    assert 0.0 <= q0 <= 1.0                                # tests/test_metrics.py:311-344
+    assert (np.diff(np.bincount(m0)) <= 0).all()           # '0' is the largest cluster
+    assert abs(old.modularity(g, m0) - q0) < 1e-7          # our Q == independent restatement
+    assert abs(_ops.modularity(g, m0) - q0) < 1e-12
+    mo, qo, _ = old.leiden(g, seed=0)
+    assert q0 >= qo - 1e-3                                 # quality guard vs the sequential oracle
+    assert adjusted_rand_score(mo, m0) > 0.9               # reference's own flavour-vs-flavour bar is NMI > 0.9
+    assert adjusted_rand_score(m1, m0) > 0.9
+    lo, _, _ = _ops.leiden(g, resolution=0.2, seed=0)
+    hi, _, _ = _ops.leiden(g, resolution=3.0, seed=0)
+    assert lo.max() < m0.max() < hi.max()
+    two, _, i2 = _ops.leiden(g, n_iterations=2, seed=0)
+    assert i2["passes"] == 2
+
+
+def test_leiden_planted_ari(synth_small):
+    x, lab = synth_small
+    ad = sb.MiniAnnData(x)
+    sb.pp.pca(ad, n_comps=30)
+    sb.pp.neighbors(ad, n_neighbors=15)
+    sb.tl.leiden(ad, flavor="igraph", n_iterations=-1)
+    got = ad.obs["leiden"].to_numpy().astype(int)
+    mo, qo, _ = old.leiden(ad.obsp["connectivities"], seed=0)
+    assert adjusted_rand_score(mo, got) >= 0.99
+    assert adjusted_rand_score(lab, got) >= 0.99
+    assert ad.uns["leiden"]["modularity"] >= qo - 1e-3
+
+
+def test_pipeline_writebacks_match_contract(synth_small):
+    # SURVEY.md Appendix B, key by key
+    x, _ = synth_small
+    ad = sb.MiniAnnData(x[:2500])
+    with pytest.warns(UserWarning, match="Falling back to preprocessing with `sc.pp.pca`"):
+        sb.pp.neighbors(ad, n_neighbors=10, n_pcs=20)      # auto-PCA (tests/test_neighbors_key_added.py:53-61)
+    assert ad.obsm["X_pca"].shape == (2500, 20)
+    assert ad.uns["neighbors"] == dict(connectivities_key="connectivities", distances_key="distances",
+                                       params=dict(n_neighbors=10, method="umap", metric="euclidean", random_state=0, n_pcs=20))
+    d, c = ad.obsp["distances"], ad.obsp["connectivities"]
+    assert (np.diff(d.indptr) == 9).all() and (d.indptr == np.arange(0, 2500 * 9 + 1, 9)).all()
+    assert c.dtype == np.float32 and abs(c - c.T).max() == 0 and (c.data != 0).all()
+    sb.pp.neighbors(ad, n_neighbors=10, n_pcs=20, key_added="nb2", rng=5)
+    assert "random_state" not in ad.uns["nb2"]["params"] and ad.uns["nb2"]["distances_key"] == "nb2_distances"
+    assert (ad.obsp["nb2_connectivities"] != c).nnz == 0   # key_added equivalence (tests/test_neighbors_key_added.py:35-50)
+    sb.tl.leiden(ad, resolution=0.8, flavor="igraph", n_iterations=2, random_state=3, key_added="cl")
+    assert ad.uns["cl"]["params"] == dict(resolution=0.8, n_iterations=2, random_state=3)
+    assert str(ad.obs["cl"].dtype) == "category" and list(ad.obs["cl"].cat.categories) == [str(i) for i in range(len(ad.obs["cl"].cat.categories))]
+    sb.tl.leiden(ad, flavor="igraph", neighbors_key="nb2", restrict_to=("cl", ["0"]))
+    r = ad.obs["leiden_R"].astype(str)
+    assert (r[ad.obs["cl"] != "0"] == ad.obs["cl"].astype(str)[ad.obs["cl"] != "0"]).all()
+    assert r[ad.obs["cl"] == "0"].str.startswith("0,").all()  # tests/test_clustering.py:177-213

@@ -1,0 +1,169 @@
+"""CPU-only tests: C-ABI surface, loud failure without a GPU, host-side mirror of the reference's helpers."""
+import re
+from pathlib import Path
+
+import numpy as np
+import pandas as pd
+import pytest
+from scipy import sparse
+
+import scanpy_b200 as sb
+from oracle import knn as oknn
+from scanpy_b200 import _abi, pp, tl
+from scanpy_b200._compat import LegacyRng, MiniAnnData, accepts_legacy_random_state, seed_from_rng
+
+ROOT = Path(__file__).resolve().parent.parent
+
+
+def test_library_exports_every_declared_symbol():
+    header = (ROOT / "include" / "scanpy_b200.h").read_text()
+    declared = set(re.findall(r"\b(sb2_[a-z0-9_]+)\s*\(", header))
+    assert len(declared) >= 18
+    assert declared == set(_abi.SIGNATURES), declared ^ set(_abi.SIGNATURES)
+    lib = _abi.load()
+    for name in declared:
+        assert hasattr(lib, name)
+    assert lib.sb2_version() >= 100
+
+
+def test_no_cpu_fallback_without_gpu():
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(_abi.B200Error):
+        _abi.Context()
+    x = sparse.random(50, 40, density=0.2, format="csr", dtype=np.float32, random_state=0)
+    with pytest.raises(_abi.B200Error):
+        pp.pca(x, n_comps=5)
+    # the raw C entry point also refuses (no device) instead of computing on the host
+    import ctypes
+
+    h = ctypes.c_void_p()
+    rc = _abi.load().sb2_ctx_create(0, None, 0, ctypes.byref(h))
+    assert rc != 0 and b"CUDA" in _abi.load().sb2_last_error()
+
+
+def test_product_never_imports_oracle():
+    for py in (ROOT / "scanpy_b200").glob("*.py"):
+        src = py.read_text()
+        assert not re.search(r"^\s*(from|import)\s+oracle", src, re.M), py
+    for cu in (ROOT / "scanpy_b200" / "csrc").glob("*.cu*"):
+        assert "oracle/" not in cu.read_text().replace("// oracle", ""), cu
+
+
+def test_indices_distances_roundtrip_matches_reference_helpers():
+    # src/scanpy/neighbors/_common.py:35-98 ; tests/test_neighbors_common.py:59-103
+    rs = np.random.RandomState(0)
+    n, k = 40, 6
+    idx = np.stack([np.r_[i, rs.permutation(np.delete(np.arange(n), i))[: k - 1]] for i in range(n)])
+    dist = np.sort(rs.rand(n, k), axis=1)
+    dist[:, 0] = 0
+    m = pp._get_sparse_matrix_from_indices_distances(idx, dist, keep_self=False)
+    mo = oknn.sparse_from_indices_distances(idx, dist, keep_self=False)
+    assert (m != mo).nnz == 0 and (np.diff(m.indptr) == k - 1).all()
+    # sklearn style (self stored) -> trimmed to k; RAPIDS style (no self) -> self prepended
+    full = pp._get_sparse_matrix_from_indices_distances(idx, dist, keep_self=True)
+    i2, d2 = pp._get_indices_distances_from_sparse_matrix(full, k - 1)
+    assert i2.shape == (n, k - 1) and (i2[:, 0] == np.arange(n)).all()
+    i3, d3 = pp._get_indices_distances_from_sparse_matrix(m, k)
+    np.testing.assert_array_equal(i3, idx)
+    np.testing.assert_allclose(d3, dist)
+    with pytest.raises(AssertionError, match="first neighbor"):
+        pp._get_sparse_matrix_from_indices_distances(idx[:, 1:], dist[:, 1:], keep_self=False)
+    # ragged rows -> slow path + RuntimeWarning (src/scanpy/neighbors/_common.py:101-123,126-143)
+    rag = m.tolil(); rag[0, idx[0, 1]] = 0; rag = rag.tocsr(); rag.eliminate_zeros()
+    with pytest.warns(RuntimeWarning, match="no constant number"):
+        i4, d4 = pp._get_indices_distances_from_sparse_matrix(rag, k)
+    assert i4.shape == (n, k) and (i4[:, 0] == np.arange(n)).all()
+
+
+def test_random_state_shim():
+    # src/scanpy/_utils/random.py:182-208
+    @accepts_legacy_random_state(0)
+    def f(*, rng=None):
+        return rng
+
+    assert isinstance(f(), LegacyRng) and f().arg == 0
+    assert f(random_state=7).arg == 7
+    assert not isinstance(f(rng=3), LegacyRng)
+    with pytest.raises(TypeError):
+        f(rng=1, random_state=1)
+    assert seed_from_rng(LegacyRng(5)) == 5
+    assert seed_from_rng(np.random.default_rng(1)) == seed_from_rng(np.random.default_rng(1))
+
+
+def _adata(n=30, g=20):
+    rs = np.random.RandomState(0)
+    return MiniAnnData(sparse.csr_matrix(rs.poisson(1.0, (n, g)).astype(np.float32)))
+
+
+def test_pca_argument_errors_match_reference():
+    a = _adata()
+    with pytest.raises(NotImplementedError, match="layer`/`obsm` and `chunked"):
+        pp.pca(a, layer="x", chunked=True)  # _pca/__init__.py:201-204
+    with pytest.raises(ValueError, match="incompatible with `obsm`"):
+        pp.pca(a, mask_var=np.ones(20, bool), obsm="foo")  # :228-230
+    with pytest.raises(ValueError, match=r"Did not find `adata.var\['nope'\]`"):
+        pp.pca(a, mask_var="nope")  # get/get.py:637-646 ; tests/test_pca.py:405-423
+    with pytest.raises(ValueError, match="The shape of the mask do not match the data."):
+        pp.pca(a, mask_var=np.ones(7, bool))
+    with pytest.raises(ValueError, match="Mask array must be boolean."):
+        pp.pca(a, mask_var=np.ones(20, int))
+    with pytest.raises(ValueError, match=r"n_components=100 must be between 1 and min\(n_samples, n_features\)=20"):
+        pp.pca(a, n_comps=100)  # tests/test_pca.py:292-296
+    with pytest.raises(NotImplementedError, match="zero_center=False"):
+        pp.pca(a, zero_center=False)
+    with pytest.warns(UserWarning, match="Ignoring svd_solver='randomized'"):
+        assert pp._solver_code("randomized", n_vars=100) in (0, 1)  # _pca/__init__.py:451-467
+    assert pp._solver_code("covariance_eigh", n_vars=10**6) == 1
+    assert pp._solver_code(None, n_vars=2000) == 1 and pp._solver_code("arpack", n_vars=30000) == 0
+
+
+def test_neighbors_and_leiden_argument_errors_match_reference():
+    a = _adata()
+    with pytest.raises(ValueError, match="`method` needs to be one of"):
+        pp.neighbors(a, method="bogus")  # neighbors/__init__.py:742-744
+    with pytest.raises(ValueError, match="only with `knn = True`"):
+        pp.neighbors(a, knn=False)  # :748-751
+    with pytest.raises(ValueError, match="Unknown transformer: nope"):
+        pp.neighbors(a, transformer="nope")  # :782-787
+    with pytest.raises(NotImplementedError, match="gauss"):
+        pp.neighbors(a, method="gauss")
+    with pytest.raises(ValueError, match="Did not find X_foo"):
+        pp._choose_representation(a, use_rep="X_foo", n_pcs=None)  # tools/_utils.py:48-50
+    # tests/test_clustering.py:105-127
+    with pytest.raises(ValueError, match="flavor must be either 'igraph' or 'leidenalg', but 'foo' was passed"):
+        tl.leiden(a, flavor="foo")
+    with pytest.raises(ValueError, match="Cannot use igraph’s leiden implementation with a directed graph."):
+        tl.leiden(a, flavor="igraph", directed=True)
+    with pytest.raises(ValueError, match="Do not pass in partition_type argument when using igraph."):
+        tl.leiden(a, flavor="igraph", partition_type=object)
+    with pytest.raises(ValueError, match="You need to run `pp.neighbors` first"):
+        tl.leiden(a, flavor="igraph")  # _utils/__init__.py:980-985
+    with pytest.raises(ValueError, match="both obsp, neighbors_key"):
+        tl._choose_graph(a, "x", "y")
+
+
+def test_transformer_protocol_surface():
+    # src/scanpy/neighbors/_types.py:53-64: fit / transform / fit_transform / get_params / set_params
+    t = sb.B200KNNTransformer(n_neighbors=7)
+    assert t.get_params()["n_neighbors"] == 7
+    assert t.set_params(n_neighbors=9) is t and t.get_params()["n_neighbors"] == 9
+    for name in ("fit", "transform", "fit_transform"):
+        assert callable(getattr(t, name))
+    with pytest.raises(NotImplementedError):
+        sb.B200KNNTransformer(metric="cosine")
+
+
+def test_rename_groups_matches_reference():
+    # src/scanpy/tools/_utils_clustering.py:16-30 ; tests/test_clustering.py:177-213
+    a = _adata(6, 5)
+    a.obs["louvain"] = pd.Categorical(["0", "1", "1", "2", "1", "0"])
+    adj = sparse.csr_matrix(np.ones((6, 6), np.float32))
+    sub, ridx = tl._restrict_adjacency(a, "louvain", restrict_categories=["1"], adjacency=adj)
+    assert sub.shape == (3, 3) and ridx.tolist() == [False, True, True, False, True, False]
+    out = tl._rename_groups(a, "louvain", restrict_categories=["1"], restrict_indices=ridx, groups=np.array([0, 1, 0]))
+    assert out.tolist() == ["0", "1,0", "1,1", "2", "1,0", "0"]
+    with pytest.raises(ValueError, match="not a valid category"):
+        tl._restrict_adjacency(a, "louvain", restrict_categories=["9"], adjacency=adj)
