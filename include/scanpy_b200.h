@@ -68,6 +68,8 @@ typedef struct sb2_pca_info {
 typedef struct sb2_knn_info {
   int64_t n_uncertified;    /* query rows that needed the exact fallback */
   float max_norm;
+  float pass1_ms;           /* CUDA-event duration of knn_pass1_kernel on the ctx stream */
+  double pass1_flops;       /* 2 * n_query * n_points * d: the algorithmic flops of that launch */
 } sb2_knn_info;
 
 typedef struct sb2_leiden_info {

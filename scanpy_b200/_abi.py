@@ -38,7 +38,7 @@ class PcaInfo(ctypes.Structure):
 
 
 class KnnInfo(ctypes.Structure):
-    _fields_ = [("n_uncertified", c_int64), ("max_norm", c_float)]
+    _fields_ = [("n_uncertified", c_int64), ("max_norm", c_float), ("pass1_ms", c_float), ("pass1_flops", c_double)]
 
 
 class LeidenInfo(ctypes.Structure):

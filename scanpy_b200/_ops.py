@@ -21,10 +21,19 @@ def _torch():
     return torch
 
 
+TRANSFER = dict(h2d=0, d2h=0)  # bytes moved by the host-array entry points (bench.py's e2e accounting)
+
+
+def _to_host(t) -> np.ndarray:
+    TRANSFER["d2h"] += t.numel() * t.element_size()
+    return t.cpu().numpy()
+
+
 def _to_device(arr: np.ndarray, *, pin: bool = True):
     """numpy -> CUDA tensor through a pinned staging buffer (async H2D on the current stream)."""
     torch = _torch()
     t = torch.from_numpy(np.ascontiguousarray(arr))
+    TRANSFER["h2d"] += t.numel() * t.element_size()
     if pin and t.numel() > 0:
         try:
             t = t.pin_memory()
@@ -66,8 +75,8 @@ def pca_csr(x, n_comps: int, *, solver: int = 0, max_iter: int = 0, tol: float =
     d_indptr, d_indices, d_data = csr_to_device(x)
     out = pca_csr_device(ctx, d_indptr, d_indices, d_data, n, g, n_comps, solver=solver, max_iter=max_iter, tol=tol,
                          seed=seed)
-    out["X_pca"] = out["X_pca"].cpu().numpy()
-    out["components"] = out["components"].cpu().numpy()
+    out["X_pca"] = _to_host(out["X_pca"])
+    out["components"] = _to_host(out["components"])
     return out
 
 
@@ -81,7 +90,8 @@ def knn_device(ctx, d_x, n_neighbors: int, *, q0: int = 0, n_query: int | None =
     info = KnnInfo()
     check(ctx.lib.sb2_knn_l2_f32(ctx.handle, n, d, ptr(d_x), q0, n_query, n_neighbors, ptr(idx), ptr(dist),
                                  byref(info)))
-    return idx, dist, dict(n_uncertified=int(info.n_uncertified), max_norm=float(info.max_norm))
+    return idx, dist, dict(n_uncertified=int(info.n_uncertified), max_norm=float(info.max_norm),
+                           pass1_ms=float(info.pass1_ms), pass1_flops=float(info.pass1_flops))
 
 
 def knn(x: np.ndarray, n_neighbors: int, *, ctx=None):
@@ -89,7 +99,7 @@ def knn(x: np.ndarray, n_neighbors: int, *, ctx=None):
     ctx = ctx or _abi.default_context()
     d_x = _to_device(np.asarray(x, dtype=np.float32))
     idx, dist, info = knn_device(ctx, d_x, n_neighbors)
-    return idx.cpu().numpy(), dist.cpu().numpy(), info
+    return _to_host(idx), _to_host(dist), info
 
 
 # ------------------------------------------------------------------------------------------ graph
@@ -119,10 +129,10 @@ def fuzzy_simplicial_set(knn_indices: np.ndarray, knn_dists: np.ndarray, *, ctx=
     d_idx = _to_device(np.asarray(knn_indices, dtype=np.int32))
     d_dist = _to_device(np.asarray(knn_dists, dtype=np.float64))
     indptr, indices, data, sig, rho = fuzzy_simplicial_set_device(ctx, d_idx, d_dist, n, k, **kw)
-    ip = indptr.cpu().numpy()
-    c = sparse.csr_matrix((data.cpu().numpy(), indices.cpu().numpy(), ip if ip[-1] >= 2**31 else ip.astype(np.int32)),
+    ip = _to_host(indptr)
+    c = sparse.csr_matrix((_to_host(data), _to_host(indices), ip if ip[-1] >= 2**31 else ip.astype(np.int32)),
                           shape=(n, n))
-    return c, sig.cpu().numpy(), rho.cpu().numpy()
+    return c, _to_host(sig), _to_host(rho)
 
 
 def leiden_device(ctx, d_indptr, d_indices, d_weights, n: int, *, resolution: float = 1.0, n_iterations: int = -1,
@@ -146,7 +156,7 @@ def leiden(adj, *, resolution: float = 1.0, n_iterations: int = -1, seed: int = 
     member, q, nc, info = leiden_device(ctx, d_indptr, d_indices, d_w, n, resolution=resolution,
                                         n_iterations=n_iterations, seed=seed)
     info["n_communities"] = nc
-    return member.cpu().numpy(), q, info
+    return _to_host(member), q, info
 
 
 def modularity(adj, membership, *, resolution: float = 1.0, ctx=None) -> float:

@@ -417,6 +417,12 @@ extern "C" int32_t sb2_knn_l2_f32(sb2_ctx* ctx, int64_t n_points, int32_t d, con
     knn_prep_kernel<<<(unsigned)n_tiles, 256, smem, st>>>(d_x, n_points, d, Xt, maxnorm);
     SB2_LAUNCH_CHECK(ctx);
   }
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  if (info) {
+    SB2_CUDA(cudaEventCreate(&ev0));
+    SB2_CUDA(cudaEventCreate(&ev1));
+    SB2_CUDA(cudaEventRecord(ev0, st));
+  }
   {
     const int64_t q_tiles = ceil_div64(n_query, TILE);
     const size_t chunk_b = (size_t)chunk_f * 4;
@@ -434,6 +440,7 @@ extern "C" int32_t sb2_knn_l2_f32(sb2_ctx* ctx, int64_t n_points, int32_t d, con
     }
     SB2_LAUNCH_CHECK(ctx);
   }
+  if (info) SB2_CUDA(cudaEventRecord(ev1, st));
   {
     const int wpb = 8;
     knn_rescore_kernel<<<(unsigned)ceil_div64(n_query, wpb), wpb * 32, 0, st>>>(
@@ -456,6 +463,12 @@ extern "C" int32_t sb2_knn_l2_f32(sb2_ctx* ctx, int64_t n_points, int32_t d, con
     float f;
     memcpy(&f, &h_bits, 4);
     info->max_norm = sqrtf(f);
+    float ms = 0.0f;
+    SB2_CUDA(cudaEventElapsedTime(&ms, ev0, ev1));
+    info->pass1_ms = ms;
+    info->pass1_flops = 2.0 * (double)n_query * (double)n_points * (double)d;
+    cudaEventDestroy(ev0);
+    cudaEventDestroy(ev1);
   }
   return SB2_OK;
 }
