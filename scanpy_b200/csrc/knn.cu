@@ -384,7 +384,8 @@ extern "C" int32_t sb2_knn_l2_f32(sb2_ctx* ctx, int64_t n_points, int32_t d, con
                                   int64_t n_query, int32_t k, int32_t* d_idx, double* d_dist, sb2_knn_info* info) {
   SB2_CHECK_ARG(ctx && d_x && d_idx && d_dist, "null pointer");
   SB2_CHECK_ARG(n_points >= 1 && n_points < (int64_t)INT32_MAX - TILE, "n_points");
-  SB2_CHECK_ARG(d >= 1 && d <= 256, "d must be in [1,256]");
+  // a query tile + two candidate stages of (d+1)*512 B must fit the 227 KB of shared memory
+  SB2_CHECK_ARG(d >= 1 && d <= 150, "d must be in [1,150]");
   SB2_CHECK_ARG(k >= 1 && k <= LISTM - 2 && k <= n_points, "k must be in [1,30] and <= n_points");
   SB2_CHECK_ARG(q0 >= 0 && n_query >= 0 && q0 + n_query <= n_points, "query range");
   SB2_CHECK_ARG(q0 % TILE == 0, "q0 must be a multiple of 128");
