@@ -22,9 +22,11 @@
 //   knn_fallback_kernel rows without a certificate (ties, duplicates, pathological scales) are
 //                       recomputed exactly in fp64 against all points.
 #include <float.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "common.cuh"
+#include "knn_internal.cuh"
 
 namespace {
 
@@ -227,7 +229,8 @@ __device__ __forceinline__ bool lex_less(double ka, int ia, double kb, int ib) {
 
 __global__ void knn_rescore_kernel(const float* __restrict__ X, int64_t n_points, int d, int64_t q0, int64_t n_query,
                                    int k, const float* __restrict__ cand_score, const int32_t* __restrict__ cand_idx,
-                                   const unsigned int* __restrict__ maxnorm_bits, int32_t* __restrict__ idx_out,
+                                   const unsigned int* __restrict__ maxnorm_bits, const float* __restrict__ inv_s2,
+                                   double eps_coef, int32_t* __restrict__ idx_out,
                                    double* __restrict__ dist_out, int32_t* __restrict__ work_q,
                                    double* __restrict__ work_ub, unsigned long long* __restrict__ work_cnt) {
   const int lane = threadIdx.x & 31;
@@ -269,15 +272,18 @@ __global__ void knn_rescore_kernel(const float* __restrict__ X, int64_t n_points
   // row maximum up to rounding, but a flood of duplicates can push it out) the row is not certified.
   const bool self_first = __shfl_sync(0xffffffffu, id, 0) == (int32_t)q;
   const double kth = __shfl_sync(0xffffffffu, key, k - 1);
-  const float s32 = __shfl_sync(0xffffffffu, cs, 31);  // proposals are stored best..worst
-  const int32_t i32 = __shfl_sync(0xffffffffu, ci, 31);
+  // worst proposal score (lists may be unsorted) and whether all 32 slots are in use
+  float s32 = ci >= 0 ? cs : INFINITY;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s32 = fminf(s32, __shfl_xor_sync(0xffffffffu, s32, o));
+  const bool list_full = __all_sync(0xffffffffu, ci >= 0);
   bool certified;
-  if (i32 < 0) {
+  if (!list_full) {
     certified = true;  // fewer than 32 points exist: the proposal list is the whole data set
   } else {
     const double R = sqrt((double)__uint_as_float(*maxnorm_bits));
-    const double eps = 1.5 * (double)(d + 2) * 5.9604644775390625e-08 * (0.5 * R * R + sqrt(qn) * R);
-    const double bound = qn - 2.0 * ((double)s32 + eps);
+    const double eps = eps_coef * (0.5 * R * R + sqrt(qn) * R);
+    const double bound = qn - 2.0 * ((double)s32 * (inv_s2 ? (double)*inv_s2 : 1.0) + eps);
     certified = self_first && (kth < bound);
   }
   if (lane < k) {
@@ -424,7 +430,15 @@ extern "C" int32_t sb2_knn_l2_f32(sb2_ctx* ctx, int64_t n_points, int32_t d, con
     SB2_CUDA(cudaEventCreate(&ev1));
     SB2_CUDA(cudaEventRecord(ev0, st));
   }
-  {
+  // pass 1: tensor-core split-precision sweep (knn_tc.cu) when the concatenated K axis fits, else fp32 FFMA
+  const char* force = getenv("SB2_KNN_PASS1");
+  const bool use_tc = knn_tc_supported(d) && !(force && strcmp(force, "ffma") == 0);
+  float* inv_s2 = nullptr;
+  double eps_coef = 1.5 * (double)(d + 2) * 5.9604644775390625e-08;
+  if (use_tc) {
+    SB2_TRY(scr.alloc(&inv_s2, 4));
+    SB2_TRY(knn_tc_pass1(ctx, scr, d_x, n_points, d, maxnorm, q0, n_query, cand_score, cand_idx, inv_s2, &eps_coef));
+  } else {
     const int64_t q_tiles = ceil_div64(n_query, TILE);
     const size_t chunk_b = (size_t)chunk_f * 4;
     const size_t smem3 = chunk_b * 4 + 64, smem2 = chunk_b * 3 + 64;
@@ -445,7 +459,8 @@ extern "C" int32_t sb2_knn_l2_f32(sb2_ctx* ctx, int64_t n_points, int32_t d, con
   {
     const int wpb = 8;
     knn_rescore_kernel<<<(unsigned)ceil_div64(n_query, wpb), wpb * 32, 0, st>>>(
-        d_x, n_points, d, q0, n_query, k, cand_score, cand_idx, maxnorm, d_idx, d_dist, work_q, work_ub, work_cnt);
+        d_x, n_points, d, q0, n_query, k, cand_score, cand_idx, maxnorm, inv_s2, eps_coef, d_idx, d_dist, work_q, work_ub,
+        work_cnt);
     SB2_LAUNCH_CHECK(ctx);
   }
   {

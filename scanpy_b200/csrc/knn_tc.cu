@@ -1,0 +1,370 @@
+// knn_tc.cu — tensor-core first pass of the exact kNN (sm_100a: tcgen05.mma + TMEM + bulk-copy ring).
+//
+// Same contract as knn_pass1_kernel (knn.cu): per query keep 32 proposals whose score
+//     s(q,c) = q.c - |c|^2/2        (d^2 = |q|^2 - 2 s)
+// is largest, plus a rigorous bound on the rounding error of s, so that knn_rescore_kernel can certify
+// the exact fp64 top-k.  The GEMM-shaped middle term runs on the 5th-gen tensor cores in split
+// precision: every fp32 coordinate x (scaled by a power of two) is written as hi + lo with
+// hi = fp16(x), lo = fp16(x - hi) (22 significant bits), and
+//     q.c ~= q_hi.c_hi + q_hi.c_lo + q_lo.c_hi
+// is ONE fp16 MMA over a concatenated K axis  A = [q_hi | q_hi | q_lo | 1 1 1],
+// B = [c_hi | c_lo | c_hi | h0 h1 h2]  with h0+h1+h2 = -|c|^2/2 (three-way fp16 split), fp32
+// accumulation in TMEM.  K = 3d+3 padded to a multiple of 16 (d = 50 -> 160: ten k-steps).
+//
+// knn_tc_prep_kernel   X[n,d] -> per 128-point tile one A image and one B image, stored exactly as the
+//                      UMMA "no-swizzle, K-major" shared-memory layout wants them (8x8 fp16 core
+//                      matrices; K-chunk-major), so a tile is staged by ONE 1-D bulk (TMA) copy.
+// knn_pass1_tc_kernel  CTA = 256 queries (two M=128 halves) x all candidate tiles (N=128 each).
+//                      warp 0   : producer, cp.async.bulk ring (3 stages x 40 KB) on mbarriers
+//                      warp 1   : TMEM allocator + single-thread tcgen05.mma issuer; per candidate tile
+//                                 2 x 10 MMAs (128x128x16) into one of two 256-column accumulator
+//                                 buffers; tcgen05.commit releases the smem stage and publishes the buffer
+//                      warps 2-9: epilogue; thread <-> one query row (TMEM lane); tcgen05.ld 32 columns
+//                                 at a time, one FSETP per element against the row's 32nd-best score;
+//                                 survivors (~300 per row over the whole sweep) go to the row's
+//                                 32-entry list in global memory (L2-resident, replace-the-minimum).
+// Candidate images are re-read by every CTA from L2: 40 KB per 256x128 tile pair => ~5 TB/s at the
+// tensor-pipe rate; 256 queries per CTA (not 128) is what keeps that under the L2 bandwidth.
+#include <cuda_fp16.h>
+#include <float.h>
+
+#include "common.cuh"
+#include "knn_internal.cuh"
+
+namespace {
+
+constexpr int TM = 128;           // rows per operand tile (UMMA M and N)
+constexpr int LISTM = 32;
+constexpr int NSTAGE = 3;
+constexpr int TC_THREADS = 320;   // 10 warps
+constexpr uint32_t SBO = 128;     // bytes between 8-row groups (core matrices contiguous)
+constexpr uint32_t LBO = TM * 16; // bytes between K-chunks (8 fp16) : [kc][row-group][8][8]
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE_%=;\n"
+      "bra WAIT_%=;\n"
+      "DONE_%=:\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// UMMA shared-memory descriptor, no swizzle, K-major (cute::UMMA::SmemDescriptor bit layout)
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);            // start address   [0,14)
+  d |= (uint64_t)((LBO >> 4) & 0x3FFFu) << 16;         // leading byte offset (K direction) [16,30)
+  d |= (uint64_t)((SBO >> 4) & 0x3FFFu) << 32;         // stride byte offset (M/N direction) [32,46)
+  d |= (uint64_t)1 << 46;                              // descriptor version (Blackwell) [46,48)
+  return d;                                            // base_offset 0, lbo_mode 0, layout_type 0 = SWIZZLE_NONE
+}
+// instruction descriptor: D=F32, A=B=F16, both K-major, N=128, M=128 (cute::UMMA::InstrDescriptor bit layout)
+constexpr uint32_t IDESC = (1u << 4) | (0u << 7) | (0u << 10) | (0u << 15) | (0u << 16) | ((128u >> 3) << 17) | ((128u >> 4) << 24);
+
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d),
+      "l"(da), "l"(db), "r"(IDESC), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+        "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+        "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// ------------------------------------------------------------------------------------------------
+// scale: power of two s with s*R in [100, 200]  ->  fp16 range is safe for coordinates and for s^2 R^2/2
+__device__ __forceinline__ float tc_scale_from_maxnorm(unsigned int maxnorm_bits) {
+  const float R = sqrtf(__uint_as_float(maxnorm_bits));
+  if (!(R > 0.0f) || !isfinite(R)) return 1.0f;
+  int e = (int)floorf(log2f(200.0f / R));
+  e = max(-60, min(60, e));
+  return exp2f((float)e);
+}
+
+__global__ void __launch_bounds__(256)
+knn_tc_prep_kernel(const float* __restrict__ X, int64_t n, int d, int kpad, const unsigned int* __restrict__ maxnorm_bits,
+                   __half* __restrict__ Aimg, __half* __restrict__ Bimg, float* __restrict__ inv_s2) {
+  const int64_t t = blockIdx.x;
+  const float s = tc_scale_from_maxnorm(*maxnorm_bits);
+  if (t == 0 && threadIdx.x == 0) *inv_s2 = 1.0f / (s * s);
+  __shared__ __half hn3[TM][3];
+  // per-row -|x|^2 s^2 / 2, three-way fp16 split
+  if (threadIdx.x < TM) {
+    const int64_t p = t * TM + threadIdx.x;
+    __half h0 = __float2half_rn(-60000.0f), h1 = __float2half_rn(0.0f), h2 = __float2half_rn(0.0f);
+    if (p < n) {
+      double acc = 0.0;
+      for (int k = 0; k < d; ++k) {
+        const double v = (double)X[p * d + k] * (double)s;
+        acc += v * v;
+      }
+      const double hn = -0.5 * acc;
+      h0 = __float2half_rn((float)hn);
+      const double r1 = hn - (double)__half2float(h0);
+      h1 = __float2half_rn((float)r1);
+      h2 = __float2half_rn((float)(r1 - (double)__half2float(h1)));
+    }
+    hn3[threadIdx.x][0] = h0; hn3[threadIdx.x][1] = h1; hn3[threadIdx.x][2] = h2;
+  }
+  __syncthreads();
+  const int nkc = kpad / 8;
+  const size_t img = (size_t)TM * kpad;  // halves per image
+  __half* Aout = Aimg + (size_t)t * img;
+  __half* Bout = Bimg + (size_t)t * img;
+  for (int i = threadIdx.x; i < TM * nkc; i += blockDim.x) {
+    const int kc = i / TM, r = i % TM;
+    const int64_t p = t * TM + r;
+    __align__(16) __half a8[8];
+    __align__(16) __half b8[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int e = kc * 8 + j;
+      __half av = __float2half_rn(0.0f), bv = av;
+      if (p < n) {
+        if (e < 3 * d) {
+          const int seg = e / d, k = e - seg * d;
+          const float xs = X[p * d + k] * s;
+          const __half hi = __float2half_rn(xs);
+          const __half lo = __float2half_rn(xs - __half2float(hi));
+          av = seg == 2 ? lo : hi;   // A = [hi | hi | lo]
+          bv = seg == 1 ? lo : hi;   // B = [hi | lo | hi]
+        } else if (e < 3 * d + 3) {
+          av = __float2half_rn(1.0f);
+          bv = hn3[r][e - 3 * d];
+        }
+      } else if (e == 3 * d) {
+        bv = hn3[r][0];  // padding candidates: score -60000 (padding queries are all-zero rows)
+      }
+      a8[j] = av; b8[j] = bv;
+    }
+    const size_t off = ((size_t)kc * LBO + (size_t)(r >> 3) * SBO + (size_t)(r & 7) * 16) / 2;  // in halves
+    *reinterpret_cast<uint4*>(Aout + off) = *reinterpret_cast<const uint4*>(a8);
+    *reinterpret_cast<uint4*>(Bout + off) = *reinterpret_cast<const uint4*>(b8);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+struct RowList {
+  float tau;
+  int cnt;
+  int minpos;
+};
+__device__ __noinline__ void list_insert(RowList* st, float* __restrict__ sc, int32_t* __restrict__ id, float v,
+                                         int32_t cand, int32_t n_points) {
+  if (cand >= n_points || !(v > st->tau)) return;
+  if (st->cnt < LISTM) {
+    sc[st->cnt] = v;
+    id[st->cnt] = cand;
+    st->cnt++;
+    if (st->cnt < LISTM) return;
+  } else {
+    sc[st->minpos] = v;
+    id[st->minpos] = cand;
+  }
+  float m = sc[0];
+  int mp = 0;
+#pragma unroll 4
+  for (int i = 1; i < LISTM; ++i) {
+    const float x = sc[i];
+    if (x < m) { m = x; mp = i; }
+  }
+  st->tau = m;
+  st->minpos = mp;
+}
+
+__global__ void __launch_bounds__(TC_THREADS, 1)
+knn_pass1_tc_kernel(const __half* __restrict__ Aimg, const __half* __restrict__ Bimg, int kpad, int64_t n_btiles,
+                    int64_t qtile0, int64_t n_query, int32_t n_points, float* __restrict__ cand_score,
+                    int32_t* __restrict__ cand_idx) {
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  const uint32_t tile_b = (uint32_t)TM * (uint32_t)kpad * 2u;  // bytes per 128-row image
+  unsigned char* As = smem_raw;                     // 2 images (256 queries)
+  unsigned char* Bs0 = smem_raw + 2 * tile_b;       // NSTAGE images
+  uint64_t* bars = reinterpret_cast<uint64_t*>(Bs0 + (size_t)NSTAGE * tile_b);
+  uint64_t* full = bars;                  // [NSTAGE] producer -> MMA
+  uint64_t* empty = bars + NSTAGE;        // [NSTAGE] MMA (commit) -> producer
+  uint64_t* afull = bars + 2 * NSTAGE;    // [1]
+  uint64_t* tfull = bars + 2 * NSTAGE + 1;   // [2] MMA (commit) -> epilogue
+  uint64_t* tempty = bars + 2 * NSTAGE + 3;  // [2] epilogue -> MMA
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * NSTAGE + 5);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < NSTAGE; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    mbar_init(afull, 1);
+    for (int b = 0; b < 2; ++b) { mbar_init(&tfull[b], 1); mbar_init(&tempty[b], 8); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const int nks = kpad / 16;  // k-steps per tile
+
+  if (warp == 0) {
+    // ---------------- producer ----------------
+    if (lane == 0) {
+      mbar_expect_tx(afull, 2 * tile_b);
+      bulk_g2s(As, reinterpret_cast<const unsigned char*>(Aimg) + (size_t)(qtile0 + 2 * (int64_t)blockIdx.x) * tile_b, 2 * tile_b, afull);
+      for (int64_t c = 0; c < n_btiles; ++c) {
+        const int s = (int)(c % NSTAGE);
+        const int64_t use = c / NSTAGE;
+        if (use > 0) mbar_wait(&empty[s], (uint32_t)((use - 1) & 1));
+        mbar_expect_tx(&full[s], tile_b);
+        bulk_g2s(Bs0 + (size_t)s * tile_b, reinterpret_cast<const unsigned char*>(Bimg) + (size_t)c * tile_b, tile_b, &full[s]);
+      }
+    }
+  } else if (warp == 1) {
+    // ---------------- MMA issuer (one thread) ----------------
+    if (lane == 0) {
+      mbar_wait(afull, 0);
+      const uint32_t a_addr = smem_u32(As);
+      for (int64_t c = 0; c < n_btiles; ++c) {
+        const int s = (int)(c % NSTAGE);
+        const int b = (int)(c & 1);
+        const int64_t useb = c >> 1;
+        mbar_wait(&full[s], (uint32_t)((c / NSTAGE) & 1));
+        if (useb > 0) mbar_wait(&tempty[b], (uint32_t)((useb - 1) & 1));
+        tc_fence_after();
+        const uint32_t b_addr = smem_u32(Bs0 + (size_t)s * tile_b);
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const uint32_t tm = tmem_base + (uint32_t)(b * 256 + h * 128);
+          for (int j = 0; j < nks; ++j) {
+            const uint64_t da = umma_desc(a_addr + (uint32_t)h * tile_b + (uint32_t)j * 2u * LBO);
+            const uint64_t db = umma_desc(b_addr + (uint32_t)j * 2u * LBO);
+            umma_f16(tm, da, db, j > 0 ? 1u : 0u);
+          }
+        }
+        tc_commit(&empty[s]);   // smem stage reusable once these MMAs have read it
+        tc_commit(&tfull[b]);   // accumulators of buffer b complete
+      }
+    }
+  } else {
+    // ---------------- epilogue: thread <-> query row ----------------
+    const int e = warp - 2;                 // 0..7
+    const int h = e >> 2;                   // query half
+    const int lgrp = warp & 3;              // TMEM lane group this warp may access
+    const int row = lgrp * 32 + lane;
+    const int64_t ql = ((int64_t)blockIdx.x * 2 + h) * TM + row;  // local query index
+    const bool valid = ql < n_query;
+    float* sc = cand_score + (valid ? ql : 0) * LISTM;
+    int32_t* id = cand_idx + (valid ? ql : 0) * LISTM;
+    RowList st;
+    st.tau = valid ? -INFINITY : INFINITY;
+    st.cnt = 0;
+    st.minpos = 0;
+    for (int64_t c = 0; c < n_btiles; ++c) {
+      const int b = (int)(c & 1);
+      mbar_wait(&tfull[b], (uint32_t)((c >> 1) & 1));
+      tc_fence_after();
+      const uint32_t tbase = tmem_base + ((uint32_t)(lgrp * 32) << 16) + (uint32_t)(b * 256 + h * 128);
+      const int32_t cbase = (int32_t)(c * TM);
+#pragma unroll 1
+      for (int ch = 0; ch < 4; ++ch) {
+        uint32_t v[32];
+        tmem_ld32(tbase + (uint32_t)(ch * 32), v);
+        bool any = false;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) any |= __uint_as_float(v[j]) > st.tau;
+        if (any) {
+          // dynamic indexing into v[] would spill it: build a hit mask, then select by compare
+          unsigned hit = 0;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) hit |= (__uint_as_float(v[j]) > st.tau ? 1u : 0u) << j;
+          while (hit) {
+            const int j = __ffs(hit) - 1;
+            hit &= hit - 1;
+            float val = 0.0f;
+#pragma unroll
+            for (int jj = 0; jj < 32; ++jj) val = (jj == j) ? __uint_as_float(v[jj]) : val;
+            list_insert(&st, sc, id, val, cbase + ch * 32 + j, n_points);
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty[b]);
+    }
+    if (valid) {
+      for (int i = st.cnt; i < LISTM; ++i) { sc[i] = -INFINITY; id[i] = -1; }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+  }
+}
+
+}  // namespace
+
+bool knn_tc_supported(int d) { return 3 * d + 3 <= 160; }
+
+int32_t knn_tc_pass1(sb2_ctx* ctx, ScratchScope& scr, const float* d_x, int64_t n_points, int d,
+                     const unsigned int* d_maxnorm_bits, int64_t q0, int64_t n_query, float* cand_score,
+                     int32_t* cand_idx, float* d_inv_s2, double* eps_coef) {
+  cudaStream_t st = ctx->stream;
+  const int kpad = ((3 * d + 3 + 15) / 16) * 16;
+  int64_t n_tiles = ceil_div64(n_points, TM);
+  const int64_t n_tiles_alloc = n_tiles + (n_tiles & 1) + 2;  // A images are consumed in pairs
+  const size_t img_halves = (size_t)TM * kpad;
+  __half *Aimg, *Bimg;
+  SB2_TRY(scr.alloc(&Aimg, (size_t)n_tiles_alloc * img_halves));
+  SB2_TRY(scr.alloc(&Bimg, (size_t)n_tiles_alloc * img_halves));
+  knn_tc_prep_kernel<<<(unsigned)n_tiles_alloc, 256, 0, st>>>(d_x, n_points, d, kpad, d_maxnorm_bits, Aimg, Bimg, d_inv_s2);
+  SB2_LAUNCH_CHECK(ctx);
+  const uint32_t tile_b = (uint32_t)TM * kpad * 2;
+  const size_t smem = (size_t)(2 + NSTAGE) * tile_b + 128;
+  SB2_CHECK_ARG(smem <= ctx->prop.sharedMemPerBlockOptin, "tensor-core kNN tile does not fit shared memory");
+  SB2_CUDA(cudaFuncSetAttribute(knn_pass1_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int64_t q_ctas = ceil_div64(n_query, 2 * TM);
+  knn_pass1_tc_kernel<<<(unsigned)q_ctas, TC_THREADS, smem, st>>>(Aimg, Bimg, kpad, n_tiles, q0 / TM, n_query,
+                                                                  (int32_t)n_points, cand_score, cand_idx);
+  SB2_LAUNCH_CHECK(ctx);
+  // error of the split-precision score, relative to (R^2/2 + |q| R): operand split 3*2^-24 + dropped lo*lo 2^-24
+  // + fp16 three-way norm 2^-33 + fp32 accumulation over kpad products in the tensor pipe (bounded generously)
+  *eps_coef = 256.0 * 5.9604644775390625e-08;
+  return SB2_OK;
+}

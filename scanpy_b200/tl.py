@@ -101,8 +101,12 @@ def leiden(adata, resolution: float = 1, *, restrict_to=None, rng=None, key_adde
         cats = sorted(map(str, np.unique(groups)), key=_natkey)
         adata.obs[key_added] = pd.Categorical(values=np.asarray(groups).astype("U"), categories=cats)
     else:
-        cats = [str(c) for c in np.unique(groups)]  # natsorted('0'..'N') == numeric order
-        adata.obs[key_added] = pd.Categorical(values=groups.astype("U"), categories=cats)
+        # == pd.Categorical(values=groups.astype("U"), categories=natsorted(map(str, np.unique(groups))))
+        # (_leiden.py:210-213): labels are 0..N-1 with no gaps, natsort == numeric order, so the codes are
+        # the labels themselves; from_codes avoids materialising 1.3M Python strings
+        n_groups = int(groups.max()) + 1 if len(groups) else 0
+        cats = [str(c) for c in range(n_groups)]
+        adata.obs[key_added] = pd.Categorical.from_codes(groups.astype(np.int32), categories=cats)
     adata.uns[key_added] = {}
     adata.uns[key_added]["params"] = dict(resolution=resolution, n_iterations=n_iterations, **meta_rs)
     adata.uns[key_added]["modularity"] = modularity
