@@ -96,7 +96,7 @@ __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t da, uint64_t 
       "l"(da), "l"(db), "r"(IDESC), "r"(accumulate)
       : "memory");
 }
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+[[maybe_unused]] __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
       "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
@@ -181,32 +181,74 @@ knn_tc_prep_kernel(const float* __restrict__ X, int64_t n, int d, int kpad, cons
 }
 
 // ------------------------------------------------------------------------------------------------
+// Per-row proposal list: 32 scores in REGISTERS (4 groups of 8 with a running minimum per group), ids in
+// global memory (write-only).  tau = min of the list = the score a candidate must beat.  All indexing is
+// static (macro-expanded), so nothing spills and an insertion never waits on memory.
 struct RowList {
+  float ls[32];
+  float gm[4];
   float tau;
-  int cnt;
-  int minpos;
 };
-__device__ __noinline__ void list_insert(RowList* st, float* __restrict__ sc, int32_t* __restrict__ id, float v,
-                                         int32_t cand, int32_t n_points) {
-  if (cand >= n_points || !(v > st->tau)) return;
-  if (st->cnt < LISTM) {
-    sc[st->cnt] = v;
-    id[st->cnt] = cand;
-    st->cnt++;
-    if (st->cnt < LISTM) return;
-  } else {
-    sc[st->minpos] = v;
-    id[st->minpos] = cand;
+__device__ __forceinline__ float min8(const float* x) {
+  return fminf(fminf(fminf(x[0], x[1]), fminf(x[2], x[3])), fminf(fminf(x[4], x[5]), fminf(x[6], x[7])));
+}
+#define SB2_GROUP_INSERT(G)                                                   \
+  {                                                                           \
+    bool placed = false;                                                      \
+    _Pragma("unroll") for (int i = 0; i < 8; ++i) {                           \
+      const bool hset = !placed && (L.ls[(G) * 8 + i] == L.tau);              \
+      L.ls[(G) * 8 + i] = hset ? v : L.ls[(G) * 8 + i];                       \
+      pos = hset ? ((G) * 8 + i) : pos;                                       \
+      placed |= hset;                                                         \
+    }                                                                         \
+    L.gm[(G)] = min8(&L.ls[(G) * 8]);                                         \
   }
-  float m = sc[0];
-  int mp = 0;
-#pragma unroll 4
-  for (int i = 1; i < LISTM; ++i) {
-    const float x = sc[i];
-    if (x < m) { m = x; mp = i; }
+__device__ __forceinline__ void list_insert(RowList& L, int32_t* __restrict__ id, float v, int32_t cand) {
+  int pos = 0;
+  if (L.gm[0] == L.tau) SB2_GROUP_INSERT(0)
+  else if (L.gm[1] == L.tau) SB2_GROUP_INSERT(1)
+  else if (L.gm[2] == L.tau) SB2_GROUP_INSERT(2)
+  else SB2_GROUP_INSERT(3)
+  id[pos] = cand;
+  L.tau = fminf(fminf(L.gm[0], L.gm[1]), fminf(L.gm[2], L.gm[3]));
+}
+// examine one 32-column chunk of the row (values already in registers).  Fast path: a 3-input max tree and
+// one compare.  Rare path (about 340 times per row over a 1.3M sweep): pull out the chunk's maxima one by one
+// while they still beat tau.  Only ONE copy of the insertion code exists per call site (the while loop), so
+// the kernel stays small enough for the instruction caches.
+__device__ __forceinline__ float max32(const uint32_t (&v)[32]) {
+  float m = __uint_as_float(v[0]);
+#pragma unroll
+  for (int j = 1; j < 32; ++j) m = fmaxf(m, __uint_as_float(v[j]));
+  return m;
+}
+__device__ __forceinline__ void scan_chunk(RowList& L, int32_t* __restrict__ id, uint32_t (&v)[32], int32_t cand0,
+                                           int32_t n_points) {
+  float m = max32(v);
+  while (m > L.tau) {
+    int j = 0;
+    bool found = false;
+    const uint32_t mb = __float_as_uint(m);
+#pragma unroll
+    for (int jj = 0; jj < 32; ++jj) {
+      const bool hset = !found && (v[jj] == mb);
+      j = hset ? jj : j;
+      v[jj] = hset ? 0xff800000u : v[jj];  // knock the maximum out (-inf)
+      found |= hset;
+    }
+    if (cand0 + j < n_points) list_insert(L, id, m, cand0 + j);
+    m = max32(v);
   }
-  st->tau = m;
-  st->minpos = mp;
+}
+__device__ __forceinline__ void tmem_ld32_nowait(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+        "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+        "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr));
 }
 
 __global__ void __launch_bounds__(TC_THREADS, 1)
@@ -291,10 +333,16 @@ knn_pass1_tc_kernel(const __half* __restrict__ Aimg, const __half* __restrict__ 
     const bool valid = ql < n_query;
     float* sc = cand_score + (valid ? ql : 0) * LISTM;
     int32_t* id = cand_idx + (valid ? ql : 0) * LISTM;
-    RowList st;
-    st.tau = valid ? -INFINITY : INFINITY;
-    st.cnt = 0;
-    st.minpos = 0;
+    RowList L;
+#pragma unroll
+    for (int i = 0; i < 32; ++i) L.ls[i] = -INFINITY;
+#pragma unroll
+    for (int g = 0; g < 4; ++g) L.gm[g] = -INFINITY;
+    L.tau = valid ? -INFINITY : INFINITY;  // rows past n_query never accept anything
+    if (valid) {
+#pragma unroll
+      for (int i = 0; i < LISTM; ++i) id[i] = -1;
+    }
     for (int64_t c = 0; c < n_btiles; ++c) {
       const int b = (int)(c & 1);
       mbar_wait(&tfull[b], (uint32_t)((c >> 1) & 1));
@@ -302,33 +350,24 @@ knn_pass1_tc_kernel(const __half* __restrict__ Aimg, const __half* __restrict__ 
       const uint32_t tbase = tmem_base + ((uint32_t)(lgrp * 32) << 16) + (uint32_t)(b * 256 + h * 128);
       const int32_t cbase = (int32_t)(c * TM);
 #pragma unroll 1
-      for (int ch = 0; ch < 4; ++ch) {
-        uint32_t v[32];
-        tmem_ld32(tbase + (uint32_t)(ch * 32), v);
-        bool any = false;
-#pragma unroll
-        for (int j = 0; j < 32; ++j) any |= __uint_as_float(v[j]) > st.tau;
-        if (any) {
-          // dynamic indexing into v[] would spill it: build a hit mask, then select by compare
-          unsigned hit = 0;
-#pragma unroll
-          for (int j = 0; j < 32; ++j) hit |= (__uint_as_float(v[j]) > st.tau ? 1u : 0u) << j;
-          while (hit) {
-            const int j = __ffs(hit) - 1;
-            hit &= hit - 1;
-            float val = 0.0f;
-#pragma unroll
-            for (int jj = 0; jj < 32; ++jj) val = (jj == j) ? __uint_as_float(v[jj]) : val;
-            list_insert(&st, sc, id, val, cbase + ch * 32 + j, n_points);
-          }
+      for (int half = 0; half < 2; ++half) {
+        uint32_t va[32], vb[32];
+        tmem_ld32_nowait(tbase + (uint32_t)(half * 64), va);
+        tmem_ld32_nowait(tbase + (uint32_t)(half * 64 + 32), vb);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        if (half == 1) {
+          // the whole row slab has been read: hand the accumulator buffer back before examining the rest
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&tempty[b]);
         }
+        scan_chunk(L, id, va, cbase + half * 64, n_points);
+        scan_chunk(L, id, vb, cbase + half * 64 + 32, n_points);
       }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&tempty[b]);
     }
     if (valid) {
-      for (int i = st.cnt; i < LISTM; ++i) { sc[i] = -INFINITY; id[i] = -1; }
+#pragma unroll
+      for (int i = 0; i < LISTM; ++i) sc[i] = L.ls[i];
     }
   }
   tc_fence_before();
