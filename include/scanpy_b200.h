@@ -70,6 +70,8 @@ typedef struct sb2_knn_info {
   float max_norm;
   float pass1_ms;           /* CUDA-event duration of knn_pass1_kernel on the ctx stream */
   double pass1_flops;       /* 2 * n_query * n_points * d: the algorithmic flops of that launch */
+  double pass1_issued_flops; /* flops actually issued (tensor path: padded tiles x split-precision K axis) */
+  int32_t pass1_tensor;     /* 1 = knn_pass1_tc_kernel (tcgen05), 0 = knn_pass1_kernel (fp32 FFMA) */
 } sb2_knn_info;
 
 typedef struct sb2_leiden_info {

@@ -91,7 +91,8 @@ def knn_device(ctx, d_x, n_neighbors: int, *, q0: int = 0, n_query: int | None =
     check(ctx.lib.sb2_knn_l2_f32(ctx.handle, n, d, ptr(d_x), q0, n_query, n_neighbors, ptr(idx), ptr(dist),
                                  byref(info)))
     return idx, dist, dict(n_uncertified=int(info.n_uncertified), max_norm=float(info.max_norm),
-                           pass1_ms=float(info.pass1_ms), pass1_flops=float(info.pass1_flops))
+                           pass1_ms=float(info.pass1_ms), pass1_flops=float(info.pass1_flops),
+                           pass1_issued_flops=float(info.pass1_issued_flops), pass1_tensor=int(info.pass1_tensor))
 
 
 def knn(x: np.ndarray, n_neighbors: int, *, ctx=None):

@@ -428,8 +428,8 @@ extern "C" int32_t sb2_knn_l2_f32(sb2_ctx* ctx, int64_t n_points, int32_t d, con
   if (info) {
     SB2_CUDA(cudaEventCreate(&ev0));
     SB2_CUDA(cudaEventCreate(&ev1));
-    SB2_CUDA(cudaEventRecord(ev0, st));
   }
+  double issued_flops = 2.0 * (double)n_query * (double)n_points * (double)d;
   // pass 1: tensor-core split-precision sweep (knn_tc.cu) when the concatenated K axis fits, else fp32 FFMA
   const char* force = getenv("SB2_KNN_PASS1");
   const bool use_tc = knn_tc_supported(d) && !(force && strcmp(force, "ffma") == 0);
@@ -437,8 +437,10 @@ extern "C" int32_t sb2_knn_l2_f32(sb2_ctx* ctx, int64_t n_points, int32_t d, con
   double eps_coef = 1.5 * (double)(d + 2) * 5.9604644775390625e-08;
   if (use_tc) {
     SB2_TRY(scr.alloc(&inv_s2, 4));
-    SB2_TRY(knn_tc_pass1(ctx, scr, d_x, n_points, d, maxnorm, q0, n_query, cand_score, cand_idx, inv_s2, &eps_coef));
+    SB2_TRY(knn_tc_pass1(ctx, scr, d_x, n_points, d, maxnorm, q0, n_query, cand_score, cand_idx, inv_s2, &eps_coef, ev0,
+                         &issued_flops));
   } else {
+    if (ev0) SB2_CUDA(cudaEventRecord(ev0, st));
     const int64_t q_tiles = ceil_div64(n_query, TILE);
     const size_t chunk_b = (size_t)chunk_f * 4;
     const size_t smem3 = chunk_b * 4 + 64, smem2 = chunk_b * 3 + 64;
@@ -483,6 +485,8 @@ extern "C" int32_t sb2_knn_l2_f32(sb2_ctx* ctx, int64_t n_points, int32_t d, con
     SB2_CUDA(cudaEventElapsedTime(&ms, ev0, ev1));
     info->pass1_ms = ms;
     info->pass1_flops = 2.0 * (double)n_query * (double)n_points * (double)d;
+    info->pass1_issued_flops = issued_flops;
+    info->pass1_tensor = use_tc ? 1 : 0;
     cudaEventDestroy(ev0);
     cudaEventDestroy(ev1);
   }

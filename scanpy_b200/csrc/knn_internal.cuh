@@ -7,4 +7,5 @@ bool knn_tc_supported(int d);
 // (score_true = score * inv_s2) + the coefficient c of the error bound  eps = c * (R^2/2 + |q| R)
 int32_t knn_tc_pass1(sb2_ctx* ctx, ScratchScope& scr, const float* d_x, int64_t n_points, int d,
                      const unsigned int* d_maxnorm_bits, int64_t q0, int64_t n_query, float* cand_score,
-                     int32_t* cand_idx, float* d_inv_s2, double* eps_coef);
+                     int32_t* cand_idx, float* d_inv_s2, double* eps_coef, cudaEvent_t ev_after_prep,
+                     double* issued_flops);

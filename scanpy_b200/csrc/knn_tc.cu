@@ -383,7 +383,8 @@ bool knn_tc_supported(int d) { return 3 * d + 3 <= 160; }
 
 int32_t knn_tc_pass1(sb2_ctx* ctx, ScratchScope& scr, const float* d_x, int64_t n_points, int d,
                      const unsigned int* d_maxnorm_bits, int64_t q0, int64_t n_query, float* cand_score,
-                     int32_t* cand_idx, float* d_inv_s2, double* eps_coef) {
+                     int32_t* cand_idx, float* d_inv_s2, double* eps_coef, cudaEvent_t ev_after_prep,
+                     double* issued_flops) {
   cudaStream_t st = ctx->stream;
   const int kpad = ((3 * d + 3 + 15) / 16) * 16;
   int64_t n_tiles = ceil_div64(n_points, TM);
@@ -394,6 +395,8 @@ int32_t knn_tc_pass1(sb2_ctx* ctx, ScratchScope& scr, const float* d_x, int64_t 
   SB2_TRY(scr.alloc(&Bimg, (size_t)n_tiles_alloc * img_halves));
   knn_tc_prep_kernel<<<(unsigned)n_tiles_alloc, 256, 0, st>>>(d_x, n_points, d, kpad, d_maxnorm_bits, Aimg, Bimg, d_inv_s2);
   SB2_LAUNCH_CHECK(ctx);
+  if (ev_after_prep) SB2_CUDA(cudaEventRecord(ev_after_prep, st));
+  if (issued_flops) *issued_flops = 2.0 * (double)(ceil_div64(n_query, 2 * TM) * 2 * TM) * (double)(n_tiles * TM) * (double)kpad;
   const uint32_t tile_b = (uint32_t)TM * kpad * 2;
   const size_t smem = (size_t)(2 + NSTAGE) * tile_b + 128;
   SB2_CHECK_ARG(smem <= ctx->prop.sharedMemPerBlockOptin, "tensor-core kNN tile does not fit shared memory");

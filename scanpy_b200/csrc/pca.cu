@@ -271,6 +271,12 @@ __global__ void residual_kernel(const double* __restrict__ Z, const double* __re
   }
   if (threadIdx.x < rstep * l) atomicAdd(&res2[j], s);
 }
+// out = a*Z + b*Y + c*W  (elementwise; W may alias nothing when c == 0)
+__global__ void lincomb3_kernel(int64_t n, double a, const double* __restrict__ Z, double b, const double* __restrict__ Y,
+                                double c, const double* __restrict__ W, double* __restrict__ out) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = a * Z[i] + b * Y[i] + (c != 0.0 ? c * W[i] : 0.0);
+}
 __global__ void f64_to_f32_kernel(const double* __restrict__ s, float* __restrict__ d, int64_t n) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) d[i] = (float)s[i];
@@ -712,12 +718,20 @@ int32_t sb2_pca_csr_f32(sb2_ctx* ctx, int64_t n, int64_t n_total, int32_t g, con
   int it = 0, converged = 0;
   double max_rel = 1e300, prev_rel = 1e300;
   int stalled = 0;
-  const int check_every = solver == 1 ? 8 : 4;
+  // Chebyshev-filtered subspace iteration (Zhou & Saad): between two Rayleigh-Ritz steps the block is
+  // multiplied by a degree-m Chebyshev polynomial of A that is bounded on the unwanted interval
+  // [0, theta_l] (A is PSD; theta_l = smallest Ritz value of the block) and grows fast above it.
+  const int cheb_m = 10;
+  const int64_t blk = (int64_t)gp * l;
+  double *P0, *P1, *P2;
+  SB2_TRY(scr.alloc(&P0, (size_t)blk));
+  SB2_TRY(scr.alloc(&P1, (size_t)blk));
+  SB2_TRY(scr.alloc(&P2, (size_t)blk));
+  const unsigned lgrid = (unsigned)ceil_div64(blk, 256);
   for (;;) {
     SB2_TRY(apply_operator(w, d_V, d_Z));
     ++it;
-    const bool check = (it % check_every == 0) || it >= max_iter || it <= 1;
-    if (check) {
+    {
       SB2_TRY(tsmm_host(w, d_V, d_Z, T));
       for (int i = 0; i < l; ++i)  // symmetrise
         for (int j = i + 1; j < l; ++j) {
@@ -743,11 +757,32 @@ int32_t sb2_pca_csr_f32(sb2_ctx* ctx, int64_t n, int64_t n_total, int32_t g, con
       if (max_rel <= tol) { converged = 1; break; }
       if (it >= max_iter) break;
       // stagnation at the operator's rounding floor (fp32 SpMM passes): stop, report not converged
-      if (it > 1 && max_rel > 0.97 * prev_rel) { if (++stalled >= 3) break; } else stalled = 0;
+      if (it > 3 && max_rel > 0.97 * prev_rel) { if (++stalled >= 3) break; } else stalled = 0;
       prev_rel = max_rel;
     }
-    // next block: V <- orth(Z)
-    SB2_CUDA(cudaMemcpyAsync(d_V, d_Z, sizeof(double) * (size_t)gp * l, cudaMemcpyDeviceToDevice, st));
+    const double cut = theta[l - 1], top = theta[0];
+    if (it >= 3 && cut > 0.0 && top > 1.0001 * cut) {
+      const double e = 0.5 * cut, c = 0.5 * cut;
+      double sigma = e / (top - c);
+      const double sigma1 = sigma;
+      // Y1 = (sigma1/e) (A V - c V), reusing Z = A V from the Rayleigh-Ritz step
+      double *prev = P0, *cur = P1, *nxt = P2;
+      SB2_CUDA(cudaMemcpyAsync(prev, d_V, sizeof(double) * (size_t)blk, cudaMemcpyDeviceToDevice, st));
+      lincomb3_kernel<<<lgrid, 256, 0, st>>>(blk, sigma1 / e, d_Z, -(sigma1 / e) * c, d_V, 0.0, d_V, cur);
+      SB2_LAUNCH_CHECK(ctx);
+      for (int i = 2; i <= cheb_m && it < max_iter; ++i) {
+        const double sigma2 = 1.0 / (2.0 / sigma1 - sigma);
+        SB2_TRY(apply_operator(w, cur, d_Z));
+        ++it;
+        lincomb3_kernel<<<lgrid, 256, 0, st>>>(blk, 2.0 * sigma2 / e, d_Z, -(2.0 * sigma2 / e) * c, cur, -(sigma * sigma2), prev, nxt);
+        SB2_LAUNCH_CHECK(ctx);
+        double* t = prev; prev = cur; cur = nxt; nxt = t;
+        sigma = sigma2;
+      }
+      SB2_CUDA(cudaMemcpyAsync(d_V, cur, sizeof(double) * (size_t)blk, cudaMemcpyDeviceToDevice, st));
+    } else {
+      SB2_CUDA(cudaMemcpyAsync(d_V, d_Z, sizeof(double) * (size_t)blk, cudaMemcpyDeviceToDevice, st));
+    }
     SB2_TRY(orthonormalize(w, d_V));
   }
   // d_V now holds Ritz vectors (columns, descending theta)
