@@ -79,6 +79,27 @@ struct ScratchScope {
 
 static inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }
 
+// debug-only phase timing (SB2_TIMING=1): synchronises the stream, so never enabled in measured runs
+#include <chrono>
+#include <stdlib.h>
+struct PhaseTimer {
+  bool on;
+  cudaStream_t st;
+  std::chrono::steady_clock::time_point t0;
+  explicit PhaseTimer(cudaStream_t s) : on(getenv("SB2_TIMING") != nullptr), st(s) { reset(); }
+  void reset() {
+    if (on) { cudaStreamSynchronize(st); t0 = std::chrono::steady_clock::now(); }
+  }
+  // adds the time since the last reset()/lap() to *acc (milliseconds)
+  void lap(double* acc) {
+    if (!on) return;
+    cudaStreamSynchronize(st);
+    auto t1 = std::chrono::steady_clock::now();
+    *acc += std::chrono::duration<double, std::milli>(t1 - t0).count();
+    t0 = t1;
+  }
+};
+
 #ifdef __CUDACC__
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll

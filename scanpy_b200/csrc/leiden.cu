@@ -579,6 +579,9 @@ extern "C" int32_t sb2_leiden_csr_f32(sb2_ctx* ctx, int64_t n, const int64_t* d_
   SB2_LAUNCH_CHECK(ctx);
 
   int passes = 0, levels = 0;
+  PhaseTimer pt(st);
+  double t_lm = 0, t_rf = 0, t_agg = 0, t_fin = 0;
+  int n_lm = 0;
   if (total > 0.0) {
     for (;;) {
       // ---- one Leiden pass starting from d_membership on the level-0 graph ----
@@ -591,10 +594,14 @@ extern "C" int32_t sb2_leiden_csr_f32(sb2_ctx* ctx, int64_t n, const int64_t* d_
       ScratchScope lvl(ctx);  // aggregated graphs of this pass
       for (;;) {
         int64_t mv = 0;
+        pt.reset();
         SB2_TRY(local_move(w, L, comm, &mv));
+        pt.lap(&t_lm);
+        ++n_lm;
         pass_moves += mv;
         ++levels;
         SB2_TRY(refine(w, L, comm, ref, Kref, rsize));
+        pt.lap(&t_rf);
         // compact refined labels
         flag_nonempty_kernel<<<gridt(L.n), 256, 0, st>>>(L.n, rsize, flag);
         SB2_LAUNCH_CHECK(ctx);
@@ -640,6 +647,7 @@ extern "C" int32_t sb2_leiden_csr_f32(sb2_ctx* ctx, int64_t n, const int64_t* d_
         SB2_LAUNCH_CHECK(ctx);
         std::swap(comm, comm_next);
         L = Level{nc, indptr_new, indices_new, w_new, k_new};
+        pt.lap(&t_agg);
       }
       gather_kernel<<<gridt(n0), 256, 0, st>>>(n0, node_of, comm, d_membership);
       SB2_LAUNCH_CHECK(ctx);
@@ -651,8 +659,13 @@ extern "C" int32_t sb2_leiden_csr_f32(sb2_ctx* ctx, int64_t n, const int64_t* d_
       if (passes >= 64) break;
     }
   }
+  pt.reset();
   SB2_TRY(renumber_device(ctx, scr, n, d_membership, h_n_comms));
   SB2_TRY(quality_device(ctx, scr, n0, d_indptr, d_indices, wfx0, kfx0, total, resolution, d_membership, h_modularity));
+  pt.lap(&t_fin);
+  if (pt.on)
+    fprintf(stderr, "[sb2 leiden] n=%d passes=%d local_move %.1f ms (%d calls) refine %.1f ms aggregate %.1f ms finalize %.1f ms\n",
+            n0, passes, t_lm, n_lm, t_rf, t_agg, t_fin);
   if (info) {
     info->passes = passes;
     info->levels = levels;

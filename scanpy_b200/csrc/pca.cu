@@ -435,6 +435,8 @@ struct PcaWork {
   double* d_S;      // [l x l]
   double* d_M;      // [l x l]
   double* d_tmp;    // [g x l]
+  int g_real;       // un-padded feature count
+  Rng* rng;         // refills rank-deficient blocks
 };
 
 int32_t launch_spmm(sb2_ctx* ctx, int64_t n, int l, const int64_t* indptr, const int32_t* indices, const float* data,
@@ -491,21 +493,51 @@ int32_t right_mult_inplace(PcaWork& w, double* A, const std::vector<double>& hM)
 // orthonormalise the columns of A (g x l): CholeskyQR, twice; eigen-based fallback if rank deficient
 int32_t orthonormalize(PcaWork& w, double* A) {
   const int l = w.l;
-  std::vector<double> S, M;
-  for (int pass = 0; pass < 2; ++pass) {
-    SB2_TRY(tsmm_host(w, A, A, S));
-    if (!chol_inverse_upper(S, l, M)) {
-      std::vector<double> ev, W;
-      jacobi_eigh(S, l, ev, W);
-      double emax = 0.0;
-      for (double e : ev) emax = std::max(emax, e);
-      M.assign((size_t)l * l, 0.0);
-      for (int j = 0; j < l; ++j) {
-        const double sc = ev[j] > 1e-12 * emax ? 1.0 / sqrt(ev[j]) : 0.0;  // null directions -> zero columns
-        for (int i = 0; i < l; ++i) M[(size_t)i * l + j] = W[(size_t)i * l + j] * sc;
+  std::vector<double> S, M, dsc(l);
+  for (int attempt = 0; attempt < 3; ++attempt) {
+    std::vector<int> dropped;
+    for (int pass = 0; pass < 2; ++pass) {
+      SB2_TRY(tsmm_host(w, A, A, S));
+      // column scaling first: after a Chebyshev filter the columns differ by many orders of magnitude
+      // (each is amplified by p(theta_j)), which would make the Gram matrix numerically singular although the
+      // columns are nearly orthogonal.  S' = D^-1/2 S D^-1/2 has a unit diagonal.
+      for (int j = 0; j < l; ++j) dsc[j] = S[(size_t)j * l + j] > 0.0 ? 1.0 / sqrt(S[(size_t)j * l + j]) : 0.0;
+      for (int i = 0; i < l; ++i)
+        for (int j = 0; j < l; ++j) S[(size_t)i * l + j] *= dsc[i] * dsc[j];
+      for (int j = 0; j < l; ++j)
+        if (dsc[j] == 0.0) S[(size_t)j * l + j] = 1.0;  // all-zero column stays zero
+      if (!chol_inverse_upper(S, l, M)) {
+        std::vector<double> ev, W;
+        jacobi_eigh(S, l, ev, W);
+        double emax = 0.0;
+        for (double e : ev) emax = std::max(emax, e);
+        M.assign((size_t)l * l, 0.0);
+        for (int j = 0; j < l; ++j) {
+          const double sc = ev[j] > 1e-12 * emax ? 1.0 / sqrt(ev[j]) : 0.0;  // null directions -> zero columns
+          for (int i = 0; i < l; ++i) M[(size_t)i * l + j] = W[(size_t)i * l + j] * sc;
+        }
+      }
+      for (int i = 0; i < l; ++i)
+        for (int j = 0; j < l; ++j) M[(size_t)i * l + j] *= dsc[i];  // A D^-1/2 M'
+      SB2_TRY(right_mult_inplace(w, A, M));
+      if (pass == 1) {
+        for (int j = 0; j < l; ++j) {
+          bool zero = true;
+          for (int i = 0; i < l && zero; ++i) zero = M[(size_t)i * l + j] == 0.0;
+          if (zero) dropped.push_back(j);
+        }
       }
     }
-    SB2_TRY(right_mult_inplace(w, A, M));
+    // directions lost to rank deficiency are replaced by fresh random vectors (only while the feature space
+    // can still hold l independent directions) and the block is orthonormalised again
+    if (dropped.empty() || w.g_real < l || attempt == 2) break;
+    std::vector<double> col((size_t)w.g);
+    for (int j : dropped) {
+      for (int r = 0; r < w.g; ++r) col[r] = r < w.g_real ? w.rng->normal() : 0.0;
+      SB2_CUDA(cudaMemcpy2DAsync(A + j, sizeof(double) * l, col.data(), sizeof(double), sizeof(double), (size_t)w.g,
+                                 cudaMemcpyHostToDevice, w.st));
+      SB2_CUDA(cudaStreamSynchronize(w.st));
+    }
   }
   return SB2_OK;
 }
@@ -703,9 +735,11 @@ int32_t sb2_pca_csr_f32(sb2_ctx* ctx, int64_t n, int64_t n_total, int32_t g, con
   SB2_CUDA(cudaFuncSetAttribute(right_mult_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(double) * l * l)));
 
   // ---- start block (identical on every rank: same seed) ----
+  Rng rng(seed);
+  w.rng = &rng;
+  w.g_real = g;
   {
     std::vector<double> hv((size_t)gp * l, 0.0);
-    Rng rng(seed);
     for (int r = 0; r < g; ++r)
       for (int j = 0; j < l; ++j) hv[(size_t)r * l + j] = rng.normal();
     SB2_CUDA(cudaMemcpyAsync(d_V, hv.data(), sizeof(double) * (size_t)gp * l, cudaMemcpyHostToDevice, st));
@@ -754,14 +788,22 @@ int32_t sb2_pca_csr_f32(sb2_ctx* ctx, int64_t n, int64_t n_total, int32_t g, con
       max_rel = 0.0;
       const double th1 = std::max(theta[0], 1e-300);
       for (int j = 0; j < k; ++j) max_rel = std::max(max_rel, sqrt(std::max(hres[j], 0.0)) / th1);
-      if (max_rel <= tol) { converged = 1; break; }
+      if (max_rel <= tol && theta[k - 1] > 0.0) { converged = 1; break; }
       if (it >= max_iter) break;
       // stagnation at the operator's rounding floor (fp32 SpMM passes): stop, report not converged
       if (it > 3 && max_rel > 0.97 * prev_rel) { if (++stalled >= 3) break; } else stalled = 0;
       prev_rel = max_rel;
     }
     const double cut = theta[l - 1], top = theta[0];
+    // degree: the filter amplifies the top of the wanted spectrum by T_m(x0), x0 = (top - c)/e, relative to the
+    // cut; beyond ~1e7 the columns next to the cut drown in rounding noise of the dominant directions, so m is
+    // capped by acosh(1e7)/acosh(x0) (a wide spectrum gets a low degree, a flat one the full cheb_m)
+    int m_use = 0;
     if (it >= 3 && cut > 0.0 && top > 1.0001 * cut) {
+      const double x0 = 2.0 * top / cut - 1.0;
+      m_use = std::min(cheb_m, (int)floor(acosh(1e7) / acosh(x0)));
+    }
+    if (m_use >= 2) {
       const double e = 0.5 * cut, c = 0.5 * cut;
       double sigma = e / (top - c);
       const double sigma1 = sigma;
@@ -770,7 +812,7 @@ int32_t sb2_pca_csr_f32(sb2_ctx* ctx, int64_t n, int64_t n_total, int32_t g, con
       SB2_CUDA(cudaMemcpyAsync(prev, d_V, sizeof(double) * (size_t)blk, cudaMemcpyDeviceToDevice, st));
       lincomb3_kernel<<<lgrid, 256, 0, st>>>(blk, sigma1 / e, d_Z, -(sigma1 / e) * c, d_V, 0.0, d_V, cur);
       SB2_LAUNCH_CHECK(ctx);
-      for (int i = 2; i <= cheb_m && it < max_iter; ++i) {
+      for (int i = 2; i <= m_use && it < max_iter; ++i) {
         const double sigma2 = 1.0 / (2.0 / sigma1 - sigma);
         SB2_TRY(apply_operator(w, cur, d_Z));
         ++it;
