@@ -101,7 +101,7 @@ def run_reference(a, rank, world):
     best = max(vals, key=lambda r: r["value"])
     v = float(np.mean([r["value"] for r in vals]))
     ms = 1e3 * a.n_cells / v
-    print(json.dumps(dict(impl="reference", metric=METRIC, value=v, unit=UNIT, n_gpus=a.gpus, steps=a.steps,
+    emit(json.dumps(dict(impl="reference", metric=METRIC, value=v, unit=UNIT, n_gpus=a.gpus, steps=a.steps,
                           warmup=a.warmup, ms_per_step=ms, higher_is_better=True, scaling="strong", vs_baseline=None,
                           dtype="f32", data="synthetic", config=workload_config(a, a.gpus),
                           cpu_baseline=dict(best, value=v),
@@ -268,10 +268,22 @@ def run_b200(a, rank, world, local_rank):
                             modularity=out["modularity"]))
     if world == 1 and not a.no_cpu_baseline:
         line["cpu_baseline"] = cpu_reference_sample(a)
-    print(json.dumps(line))
+    emit(json.dumps(line))
+
+
+_REAL_STDOUT = None
+
+
+def emit(line: str) -> None:
+    """The ONE JSON line goes to the real stdout; everything else (NCCL banners, library chatter) was diverted."""
+    os.write(_REAL_STDOUT if _REAL_STDOUT is not None else 1, (line + "\n").encode())
 
 
 def main():
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)  # native libraries that print to fd 1 (e.g. "NCCL version ...") now land on stderr
     a = parse_args()
     rank = int(os.environ.get("RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))

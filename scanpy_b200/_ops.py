@@ -136,6 +136,22 @@ def fuzzy_simplicial_set(knn_indices: np.ndarray, knn_dists: np.ndarray, *, ctx=
     return c, _to_host(sig), _to_host(rho)
 
 
+def knn_and_connectivities(x: np.ndarray, n_neighbors: int, *, ctx=None):
+    """Exact kNN + UMAP connectivities with the (idx, dist) lists kept on the device in between.
+    -> (indices int32 [n,k], distances float64 [n,k], connectivities scipy CSR float32)."""
+    from scipy import sparse
+
+    ctx = ctx or _abi.default_context()
+    n = x.shape[0]
+    d_x = _to_device(x)
+    d_idx, d_dist, _ = knn_device(ctx, d_x, n_neighbors)
+    indptr, indices, data, _, _ = fuzzy_simplicial_set_device(ctx, d_idx, d_dist, n, n_neighbors)
+    ip = _to_host(indptr)
+    conn = sparse.csr_matrix((_to_host(data), _to_host(indices), ip if ip[-1] >= 2**31 else ip.astype(np.int32)),
+                             shape=(n, n))
+    return _to_host(d_idx), _to_host(d_dist), conn
+
+
 def leiden_device(ctx, d_indptr, d_indices, d_weights, n: int, *, resolution: float = 1.0, n_iterations: int = -1,
                   seed: int = 0):
     torch = _torch()

@@ -119,6 +119,11 @@ decide_kernel(Level L, const int32_t* __restrict__ comm, const int32_t* __restri
   double best_gain = -1e300;
   int32_t best = -1;
   double wa = 0.0;  // weight towards own community (local moving only)
+  // swap guard, applied while candidates are collected (so the next-best admissible community is still found):
+  // a singleton may join another SINGLETON only towards the smaller id (local moving: community id, refinement:
+  // vertex id == label of a singleton); everything else is admissible
+  const bool v_single = REFINE ? true : csize[a] == 1;
+  auto allowed = [&](int32_t c) -> bool { return !(v_single && csize[c] == 1 && c > (REFINE ? v : a)); };
 
   if (deg <= 32) {
     int32_t c = -1 - lane;  // unique negative = "no neighbour"
@@ -143,7 +148,7 @@ decide_kernel(Level L, const int32_t* __restrict__ comm, const int32_t* __restri
     }
     if (c >= 0 && leader) {
       if (!REFINE && c == a) wa = (double)tot;
-      else { best_gain = (double)tot - scale * (double)K[c]; best = c; }
+      else if (allowed(c)) { best_gain = (double)tot - scale * (double)K[c]; best = c; }
     }
   } else {
     // hash slice [e0, e1): capacity = deg >= number of distinct neighbouring communities
@@ -166,6 +171,7 @@ decide_kernel(Level L, const int32_t* __restrict__ comm, const int32_t* __restri
       if (c < 0) continue;
       const double tot = (double)hvals[s];
       if (!REFINE && c == a) { wa = tot; continue; }
+      if (!allowed(c)) continue;
       const double gain = tot - scale * (double)K[c];
       if (gain > best_gain || (gain == best_gain && c < best)) { best_gain = gain; best = c; }
     }
@@ -185,13 +191,8 @@ decide_kernel(Level L, const int32_t* __restrict__ comm, const int32_t* __restri
     if (best >= 0) {
       const double stay = REFINE ? 0.0 : wa - scale * ((double)K[a] - kv);
       if (best_gain > stay + 0.5) {
-        const bool bsingle = csize[best] == 1;
-        if (!REFINE) {
-          // swap guard: two singletons may only merge towards the smaller community id
-          if (!(csize[a] == 1 && bsingle && best > a)) t = best;
-        } else {
-          if (!(bsingle && best > v)) { t = best; ts = bsingle ? 1 : 0; }
-        }
+        t = best;
+        ts = (REFINE && csize[best] == 1) ? 1 : 0;
       }
     }
     target[v] = t;
@@ -363,6 +364,7 @@ struct Work {
   double total;    // 2m in fixed units
   uint32_t seed;
   int64_t moves_total;
+  int last_sweeps;
 };
 
 inline unsigned gridw(int64_t n) { return (unsigned)ceil_div64(n, 8); }    // warp per item, 8 warps/CTA
@@ -383,9 +385,11 @@ int32_t local_move(Work& w, const Level& L, int32_t* comm, int64_t* moves_out) {
   fill_u8_kernel<<<gridt(L.n), 256, 0, w.st>>>(w.active[0], L.n, 1);
   SB2_LAUNCH_CHECK(ctx);
   int cur = 0, noskip = 0;
+  u64 prev_c = ~0ull;
   int64_t moves = 0;
   const int max_sweeps = 200;
   for (int sweep = 0; sweep < max_sweeps; ++sweep) {
+    w.last_sweeps = sweep + 1;
     SB2_CUDA(cudaMemsetAsync(w.active[cur ^ 1], 0, (size_t)L.n, w.st));
     SB2_CUDA(cudaMemsetAsync(w.counter, 0, sizeof(u64), w.st));
     decide_kernel<false><<<gridw(L.n), 256, 0, w.st>>>(L, comm, nullptr, (const int64_t*)w.K, w.csize, w.active[cur], w.gamma,
@@ -400,11 +404,17 @@ int32_t local_move(Work& w, const Level& L, int32_t* comm, int64_t* moves_out) {
     if (c == 0) {
       if (noskip) break;
       noskip = 1;  // confirm with a sweep in which every active vertex decides
+    } else if ((int64_t)c * 512 < (int64_t)L.n && (!noskip || c < prev_c)) {
+      // tail: few vertices still move, simultaneous conflicting moves are unlikely -> let every active vertex
+      // decide each sweep (halves the number of tail sweeps); falls back to half-sweeps if it stops shrinking
+      noskip = 1;
     } else {
       noskip = 0;
     }
+    prev_c = c;
   }
   *moves_out = moves;
+  if (getenv("SB2_TIMING")) fprintf(stderr, "[sb2 leiden]   local_move n=%d sweeps=%d moves=%lld\n", L.n, w.last_sweeps, (long long)moves);
   return SB2_OK;
 }
 
@@ -421,6 +431,7 @@ int32_t refine(Work& w, const Level& L, const int32_t* comm, int32_t* ref, int64
     SB2_LAUNCH_CHECK(ctx);
     u64 c = 0;
     SB2_TRY(read_counter(w, 0, &c));
+    if (getenv("SB2_TIMING")) fprintf(stderr, "[sb2 leiden]   refine n=%d round=%d merges=%llu\n", L.n, round, c);
     if (c == 0) break;
   }
   return SB2_OK;
@@ -579,6 +590,7 @@ extern "C" int32_t sb2_leiden_csr_f32(sb2_ctx* ctx, int64_t n, const int64_t* d_
   SB2_LAUNCH_CHECK(ctx);
 
   int passes = 0, levels = 0;
+  int64_t prev_higher_moves = -1;
   PhaseTimer pt(st);
   double t_lm = 0, t_rf = 0, t_agg = 0, t_fin = 0;
   int n_lm = 0;
@@ -589,8 +601,9 @@ extern "C" int32_t sb2_leiden_csr_f32(sb2_ctx* ctx, int64_t n, const int64_t* d_
       SB2_CUDA(cudaMemcpyAsync(comm, d_membership, sizeof(int32_t) * n0, cudaMemcpyDeviceToDevice, st));
       iota_kernel<<<gridt(n0), 256, 0, st>>>(node_of, n0);
       SB2_LAUNCH_CHECK(ctx);
-      int64_t pass_moves = 0;
-      levels = 0;
+      int64_t pass_moves = 0, higher_moves = 0;
+      int lev = 0;
+      bool idle_pass = false;
       ScratchScope lvl(ctx);  // aggregated graphs of this pass
       for (;;) {
         int64_t mv = 0;
@@ -599,7 +612,13 @@ extern "C" int32_t sb2_leiden_csr_f32(sb2_ctx* ctx, int64_t n, const int64_t* d_
         pt.lap(&t_lm);
         ++n_lm;
         pass_moves += mv;
-        ++levels;
+        if (lev > 0) higher_moves += mv;
+        // A pass whose level-0 sweep moves nothing, started from a partition on which the previous pass already
+        // found no move at any aggregated level, would replay that pass exactly (refinement and aggregation are
+        // deterministic functions of the partition; "no improving move exists" does not depend on the seed).
+        if (lev == 0 && mv == 0 && passes > 0 && prev_higher_moves == 0 && n_iterations < 0) { idle_pass = true; break; }
+        ++lev;
+        levels = lev;
         SB2_TRY(refine(w, L, comm, ref, Kref, rsize));
         pt.lap(&t_rf);
         // compact refined labels
@@ -649,6 +668,8 @@ extern "C" int32_t sb2_leiden_csr_f32(sb2_ctx* ctx, int64_t n, const int64_t* d_
         L = Level{nc, indptr_new, indices_new, w_new, k_new};
         pt.lap(&t_agg);
       }
+      if (idle_pass) { ++passes; break; }
+      prev_higher_moves = higher_moves;
       gather_kernel<<<gridt(n0), 256, 0, st>>>(n0, node_of, comm, d_membership);
       SB2_LAUNCH_CHECK(ctx);
       SB2_CUDA(cudaStreamSynchronize(st));

@@ -247,11 +247,18 @@ def neighbors(adata, n_neighbors: int = 15, n_pcs: int | None = None, *, distanc
         warn(f"n_obs too small: adjusting to `n_neighbors = {n_neighbors}`", UserWarning)
     x = _choose_representation(adata, use_rep=use_rep, n_pcs=n_pcs)
     if transformer is None or isinstance(transformer, str):
-        transformer = B200KNNTransformer(n_neighbors=n_neighbors, metric=metric)
-    d = transformer.fit_transform(x)
-    knn_indices, knn_distances = _get_indices_distances_from_sparse_matrix(d, n_neighbors)
+        # built-in exact kNN: (idx, dist) stay in HBM between the search and the fuzzy-set kernels, so the
+        # n x k lists cross PCIe once (device -> host) instead of three times
+        xd = x.toarray() if sparse.issparse(x) else np.asarray(x)
+        knn_indices, knn_distances, conn = _ops.knn_and_connectivities(np.ascontiguousarray(xd, dtype=np.float32),
+                                                                        min(n_neighbors, adata.shape[0]))
+        if knn_indices.shape[1] > n_neighbors:
+            knn_indices, knn_distances = knn_indices[:, :n_neighbors], knn_distances[:, :n_neighbors]
+    else:
+        d = transformer.fit_transform(x)
+        knn_indices, knn_distances = _get_indices_distances_from_sparse_matrix(d, n_neighbors)
+        conn, _, _ = _ops.fuzzy_simplicial_set(knn_indices, knn_distances)
     dist_csr = _get_sparse_matrix_from_indices_distances(knn_indices, knn_distances, keep_self=False)
-    conn, _, _ = _ops.fuzzy_simplicial_set(knn_indices, knn_distances)
 
     if key_added is None:
         key_added, conns_key, dists_key = "neighbors", "connectivities", "distances"
