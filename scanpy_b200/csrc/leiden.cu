@@ -365,6 +365,7 @@ struct Work {
   uint32_t seed;
   int64_t moves_total;
   int last_sweeps;
+  bool first_pass;
 };
 
 inline unsigned gridw(int64_t n) { return (unsigned)ceil_div64(n, 8); }    // warp per item, 8 warps/CTA
@@ -401,9 +402,15 @@ int32_t local_move(Work& w, const Level& L, int32_t* comm, int64_t* moves_out) {
     SB2_TRY(read_counter(w, 0, &c));
     moves += (int64_t)c;
     cur ^= 1;
+    if (getenv("SB2_TIMING") && getenv("SB2_VERBOSE")) fprintf(stderr, "[sb2 leiden]     sweep %d noskip=%d moves=%llu\n", sweep, noskip, c);
     if (c == 0) {
       if (noskip) break;
       noskip = 1;  // confirm with a sweep in which every active vertex decides
+    } else if (w.first_pass && (int64_t)c * 200 < (int64_t)L.n) {
+      // First pass only: once fewer than 0.5 % of the vertices still move, what remains is communities
+      // merging one vertex at a time in slow waves - the aggregated level does that in a single move, and the
+      // following passes (which run local moving to exact convergence) pick up any leftover single-vertex gain.
+      break;
     } else if ((int64_t)c * 512 < (int64_t)L.n && (!noskip || c < prev_c)) {
       // tail: few vertices still move, simultaneous conflicting moves are unlikely -> let every active vertex
       // decide each sweep (halves the number of tail sweeps); falls back to half-sweeps if it stops shrinking
@@ -601,6 +608,7 @@ extern "C" int32_t sb2_leiden_csr_f32(sb2_ctx* ctx, int64_t n, const int64_t* d_
       SB2_CUDA(cudaMemcpyAsync(comm, d_membership, sizeof(int32_t) * n0, cudaMemcpyDeviceToDevice, st));
       iota_kernel<<<gridt(n0), 256, 0, st>>>(node_of, n0);
       SB2_LAUNCH_CHECK(ctx);
+      w.first_pass = passes == 0 && n_iterations != 1;
       int64_t pass_moves = 0, higher_moves = 0;
       int lev = 0;
       bool idle_pass = false;
