@@ -214,6 +214,57 @@ def _choose_representation(adata, *, use_rep: str | None, n_pcs: int | None):
     raise ValueError(f"Did not find {use_rep} in `.obsm.keys()`. You need to compute it first.")
 
 
+def _get_indices_distances_from_dense_matrix(d, n_neighbors: int):
+    """src/scanpy/neighbors/_common.py:63-71."""
+    sample_range = np.arange(d.shape[0])[:, None]
+    indices = np.argpartition(d, n_neighbors - 1, axis=1)[:, :n_neighbors]
+    indices = indices[sample_range, np.argsort(d[sample_range, indices])]
+    return indices, d[sample_range, indices]
+
+
+def _write_neighbors(adata, key_added, *, dist, conn, params):
+    if key_added is None:
+        key_added, conns_key, dists_key = "neighbors", "connectivities", "distances"
+    else:
+        conns_key, dists_key = f"{key_added}_connectivities", f"{key_added}_distances"
+    adata.uns[key_added] = dict(connectivities_key=conns_key, distances_key=dists_key, params=params)
+    adata.obsp[dists_key] = dist
+    adata.obsp[conns_key] = conn
+    return key_added, dists_key, conns_key
+
+
+def _neighbors_from_distances(adata, n_neighbors, *, distances, method, metric, metric_kwds, use_rep, n_pcs, knn,
+                              meta_rs, key_added, copy):
+    """Precomputed `distances=`: skip PCA and the search, compute connectivities only
+    (src/scanpy/neighbors/__init__.py:232-270, :675-701)."""
+    ignored = {name for name, val, default in (("use_rep", use_rep, None), ("knn", knn, True), ("n_pcs", n_pcs, None),
+                                                 ("metric_kwds", dict(metric_kwds), {})) if val != default}
+    if meta_rs.get("random_state") != 0:
+        ignored.add("rng/random_state")
+        meta_rs = {k: v for k, v in meta_rs.items() if k != "random_state"}
+    if ignored:
+        warn(f"Parameter(s) ignored if `distances` is given: {ignored}", UserWarning)
+    if callable(metric):
+        raise TypeError("`metric` must be a string if `distances` is given.")
+    start = log_start("computing connectivities")
+    adata = adata.copy() if copy else adata
+    if sparse.issparse(distances):
+        distances = distances.tocsr(copy=True)
+        distances.setdiag(0)
+        distances.eliminate_zeros()
+        knn_indices, knn_distances = _get_indices_distances_from_sparse_matrix(distances, n_neighbors)
+    else:
+        distances = np.asarray(distances).copy()
+        np.fill_diagonal(distances, 0)
+        knn_indices, knn_distances = _get_indices_distances_from_dense_matrix(distances, n_neighbors)
+    conn, _, _ = _ops.fuzzy_simplicial_set(knn_indices.astype(np.int32), knn_distances.astype(np.float64))
+    params = dict(n_neighbors=n_neighbors, method=method, metric=metric, **meta_rs,
+                  **({} if not metric_kwds else dict(metric_kwds=metric_kwds)))
+    key_added, dists_key, conns_key = _write_neighbors(adata, key_added, dist=distances, conn=conn, params=params)
+    log_done(start, f"added to `.uns[{key_added!r}]`, `.obsp[{dists_key!r}]`, `.obsp[{conns_key!r}]`")
+    return adata if copy else None
+
+
 @accepts_legacy_random_state(0)
 def neighbors(adata, n_neighbors: int = 15, n_pcs: int | None = None, *, distances=None, use_rep: str | None = None,
               knn: bool = True, method: str = "umap", transformer=None, metric: str | None = None,
@@ -227,10 +278,12 @@ def neighbors(adata, n_neighbors: int = 15, n_pcs: int | None = None, *, distanc
         raise ValueError("`method` needs to be one of ('umap', 'gauss', 'jaccard').")
     if method in ("gauss", "jaccard"):
         raise NotImplementedError(f"method={method!r} connectivities are not implemented in scanpy_b200.")
+    if distances is not None:
+        return _neighbors_from_distances(adata, n_neighbors, distances=distances, method=method, metric=metric,
+                                         metric_kwds=metric_kwds, use_rep=use_rep, n_pcs=n_pcs, knn=knn,
+                                         meta_rs=meta_rs, key_added=key_added, copy=copy)
     if not knn:
         raise ValueError(f"`method = {method!r} only with `knn = True`.")
-    if distances is not None:
-        raise NotImplementedError("precomputed `distances=` are not implemented in scanpy_b200.pp.neighbors")
     if metric is None:
         metric = "euclidean"
     if callable(metric) or metric not in ("euclidean", "l2"):

@@ -290,3 +290,34 @@ def test_pipeline_writebacks_match_contract(synth_small):
     r = ad.obs["leiden_R"].astype(str)
     assert (r[ad.obs["cl"] != "0"] == ad.obs["cl"].astype(str)[ad.obs["cl"] != "0"]).all()
     assert r[ad.obs["cl"] == "0"].str.startswith("0,").all()  # tests/test_clustering.py:177-213
+
+
+def test_neighbors_precomputed_distances_and_use_rep(synth_small):
+    # recompute-from-stored-distances equivalence (tests/test_neighbors.py:275-296) and use_rep (:251-261)
+    x, _ = synth_small
+    ad = sb.MiniAnnData(x[:1200])
+    sb.pp.pca(ad, n_comps=15)
+    sb.pp.neighbors(ad, n_neighbors=12)
+    ad2 = sb.MiniAnnData(x[:1200])
+    with pytest.warns(UserWarning, match="ignored if `distances` is given"):
+        sb.pp.neighbors(ad2, n_neighbors=12, distances=ad.obsp["distances"], n_pcs=5)
+    np.testing.assert_allclose(ad2.obsp["connectivities"].toarray(), ad.obsp["connectivities"].toarray(), rtol=1e-5)
+    assert ad2.uns["neighbors"]["params"]["method"] == "umap"
+    np.testing.assert_allclose(ad2.obsp["distances"].toarray(), ad.obsp["distances"].toarray(), rtol=1e-5)
+    p, p_d = (dict(a.uns["neighbors"]["params"]) for a in (ad, ad2))
+    assert p.pop("metric") == "euclidean" and p_d.pop("metric") is None and p == p_d
+    # a dense precomputed matrix means ALL pairwise distances (src/scanpy/neighbors/_common.py:63-71)
+    from sklearn.metrics import pairwise_distances
+    full = pairwise_distances(ad.obsm["X_pca"].astype(np.float64))
+    ad3 = sb.MiniAnnData(x[:1200])
+    sb.pp.neighbors(ad3, n_neighbors=12, distances=full)
+    np.testing.assert_allclose(ad3.obsp["connectivities"].toarray(), ad.obsp["connectivities"].toarray(), rtol=1e-4, atol=1e-6)
+    ad4 = sb.MiniAnnData(x[:1200], obsm={"X_rep": ad.obsm["X_pca"].copy()})
+    sb.pp.neighbors(ad4, n_neighbors=12, use_rep="X_rep")
+    assert (ad4.obsp["distances"] != ad.obsp["distances"]).nnz == 0
+    assert ad4.uns["neighbors"]["params"]["use_rep"] == "X_rep"
+    # n_pcs slicing == PCA with fewer components (tests/test_pca.py:389-400)
+    sb.pp.neighbors(ad, n_neighbors=12, n_pcs=8, key_added="p8")
+    ad5 = sb.MiniAnnData(x[:1200], obsm={"X_pca": ad.obsm["X_pca"][:, :8].copy()})
+    sb.pp.neighbors(ad5, n_neighbors=12)
+    assert (ad5.obsp["distances"] != ad.obsp["p8_distances"]).nnz == 0
