@@ -156,6 +156,27 @@ int32_t sb2_modularity_csr_f32(sb2_ctx* ctx, int64_t n, const int64_t* d_indptr,
                                const float* d_weights, double resolution, const int32_t* d_membership,
                                double* h_modularity);
 
+/* ---- preprocessing passes in front of the path: normalize_total, log1p, HVG statistics ----
+ * sb2_csr_row_sums_f32      <- numba `_normalize_csr` (src/scanpy/preprocessing/_normalization.py:29-66): per-cell
+ *                              totals; with d_skip_cols only columns whose flag is 0 are summed
+ * sb2_csr_hiexpr_count_f32  <- same function, the `exclude_highly_expressed` branch: per-gene count of entries
+ *                              exceeding max_fraction * cell total
+ * sb2_csr_scale_rows_f32    <- axis_mul_or_truediv(x, counts_per_cell, op=truediv, allow_divide_by_zero=False)
+ *                              (src/scanpy/_utils/__init__.py:623-660), in place
+ * sb2_log1p_f32             <- np.log1p(x.data) [/ log(base)] (src/scanpy/preprocessing/_simple.py:359-380), in place
+ * sb2_csr_col_sums_f32      <- stats.mean_var(expm1(x), axis=0) inside highly_variable_genes(flavor='seurat')
+ *                              (src/scanpy/preprocessing/_highly_variable_genes.py:337-346): per-gene sum and sum of
+ *                              squares (fp64) of expm1(x * log_scale) (apply_expm1 = 1) or of x */
+int32_t sb2_csr_row_sums_f32(sb2_ctx* ctx, int64_t n, const int64_t* d_indptr, const int32_t* d_indices,
+                             const float* d_data, const int32_t* d_skip_cols, float* d_out);
+int32_t sb2_csr_hiexpr_count_f32(sb2_ctx* ctx, int64_t n, int32_t g, const int64_t* d_indptr, const int32_t* d_indices,
+                                 const float* d_data, const float* d_row_sums, double max_fraction,
+                                 int32_t* d_counts_per_col);
+int32_t sb2_csr_scale_rows_f32(sb2_ctx* ctx, int64_t n, const int64_t* d_indptr, float* d_data, const float* d_scale);
+int32_t sb2_log1p_f32(sb2_ctx* ctx, int64_t nnz, float* d_data, double base);
+int32_t sb2_csr_col_sums_f32(sb2_ctx* ctx, int64_t nnz, int32_t g, const int32_t* d_indices, const float* d_data,
+                             int32_t apply_expm1, double log_scale, double* d_sum, double* d_sumsq);
+
 #ifdef __cplusplus
 }
 #endif

@@ -77,6 +77,13 @@ SIGNATURES = {
                                      c_void_p, POINTER(c_double), POINTER(c_int32), POINTER(LeidenInfo)]),
     "sb2_modularity_csr_f32": (c_int32, [c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_double, c_void_p,
                                          POINTER(c_double)]),
+    "sb2_csr_row_sums_f32": (c_int32, [c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "sb2_csr_hiexpr_count_f32": (c_int32, [c_void_p, c_int64, c_int32, c_void_p, c_void_p, c_void_p, c_void_p, c_double,
+                                           c_void_p]),
+    "sb2_csr_scale_rows_f32": (c_int32, [c_void_p, c_int64, c_void_p, c_void_p, c_void_p]),
+    "sb2_log1p_f32": (c_int32, [c_void_p, c_int64, c_void_p, c_double]),
+    "sb2_csr_col_sums_f32": (c_int32, [c_void_p, c_int64, c_int32, c_void_p, c_void_p, c_int32, c_double, c_void_p,
+                                       c_void_p]),
 }
 
 _lib = None

@@ -122,6 +122,35 @@ def main() -> None:
     for k, v in fx.items():
         print(k, v.shape, v.dtype)
 
+    # --- preprocessing golden: the reference's tests/test_highly_variable_genes.py:379-421 runs
+    # filter_cells -> normalize_total(1e4) -> log1p -> highly_variable_genes(flavor='seurat') on pbmc68k_reduced's
+    # `.raw.X` and compares with tests/_scripts/seurat_hvg.csv (produced by Seurat in R).  `.raw.X` is rebuilt here
+    # exactly as src/scanpy/datasets/_datasets.py:407-425 does (V1 preset).
+    import csv
+
+    from scipy import sparse
+
+    counts = sparse.csr_matrix((read_zarr_array(z, "layers/counts/data"), read_zarr_array(z, "layers/counts/indices"),
+                                read_zarr_array(z, "layers/counts/indptr")), shape=(700, 765))
+    n_counts = read_zarr_array(z, "obs/n_counts")
+    size_factors = n_counts / 1e4
+    log_counts = counts.astype(np.float32)
+    log_counts.data /= np.repeat(size_factors, np.diff(log_counts.indptr))
+    log_counts.data = np.log1p(log_counts.data)
+    log_counts.data = np.round(log_counts.data, 3)
+    log_counts[357, 715] = 4.019
+    log_counts = log_counts.tocsr()
+    with open(REF / "tests/_scripts/seurat_hvg.csv") as fh:
+        rows = list(csv.DictReader(fh))
+    np.savez_compressed(
+        OUT / "pbmc68k_raw_seurat_hvg.npz",
+        raw_data=log_counts.data.astype(np.float32), raw_indices=log_counts.indices.astype(np.int32),
+        raw_indptr=log_counts.indptr.astype(np.int32),
+        means=np.array([float(r["means"]) for r in rows]), dispersions=np.array([float(r["dispersions"]) for r in rows]),
+        dispersions_norm=np.array([float(r["dispersions_norm"]) for r in rows]),
+        highly_variable=np.array([r["highly_variable"] == "TRUE" for r in rows]))
+    print("raw X", log_counts.shape, log_counts.nnz, "seurat rows", len(rows))
+
 
 if __name__ == "__main__":
     main()

@@ -321,3 +321,52 @@ def test_neighbors_precomputed_distances_and_use_rep(synth_small):
     ad5 = sb.MiniAnnData(x[:1200], obsm={"X_pca": ad.obsm["X_pca"][:, :8].copy()})
     sb.pp.neighbors(ad5, n_neighbors=12)
     assert (ad5.obsp["distances"] != ad.obsp["p8_distances"]).nnz == 0
+
+
+# ------------------------------------------------------------------------------------------ preprocessing (8f, f2)
+def _raw_pbmc():
+    from pathlib import Path
+
+    f = np.load(Path(__file__).parent / "golden" / "pbmc68k_raw_seurat_hvg.npz")
+    return sparse.csr_matrix((f["raw_data"], f["raw_indices"], f["raw_indptr"]), shape=(700, 765)), f
+
+
+def test_preprocess_chain_matches_seurat_golden():
+    # the reference's own golden: tests/test_highly_variable_genes.py:379-421 (rtol = atol = 2e-5 there)
+    x, f = _raw_pbmc()
+    ad = sb.MiniAnnData(x.copy())
+    sb.pp.normalize_total(ad, target_sum=1e4)
+    sb.pp.log1p(ad)
+    assert ad.uns["log1p"] == {"base": None}
+    sb.pp.highly_variable_genes(ad, flavor="seurat", min_mean=0.0125, max_mean=3, min_disp=0.5)
+    np.testing.assert_array_equal(ad.var["highly_variable"].to_numpy(), f["highly_variable"])
+    for k in ("means", "dispersions", "dispersions_norm"):
+        np.testing.assert_allclose(ad.var[k].to_numpy(), f[k], rtol=2e-5, atol=2e-5)
+    # and the whole chain feeds the hot path: mask_var picks var['highly_variable'] up
+    sb.pp.pca(ad, n_comps=10)
+    assert (ad.varm["PCs"][~f["highly_variable"]] == 0).all()
+
+
+def test_normalize_total_and_log1p_match_oracle():
+    from oracle import preprocess as op
+
+    a = np.array([[3, 3, 3, 6, 6], [1, 1, 1, 2, 2], [1, 22, 1, 2, 2]], dtype=np.float32)
+    out = sb.pp.normalize_total(sb.MiniAnnData(sparse.csr_matrix(a)), target_sum=1, inplace=False)
+    np.testing.assert_allclose(out["X"].toarray(), op.normalize_total(a, target_sum=1)[0].toarray(), rtol=1e-7)
+    out = sb.pp.normalize_total(sb.MiniAnnData(sparse.csr_matrix(a)), target_sum=1, exclude_highly_expressed=True,
+                                max_fraction=0.2, inplace=False)
+    np.testing.assert_allclose(out["X"].toarray(), [[0.5, 0.5, 0.5, 1, 1], [0.5, 0.5, 0.5, 1, 1], [0.5, 11, 0.5, 1, 1]], rtol=1e-6)
+    rs = np.random.RandomState(0)
+    x = sparse.random(5000, 300, density=0.1, format="csr", random_state=rs, data_rvs=lambda s: rs.poisson(3, s) + 1).astype(np.float32)
+    x[17] = 0  # an empty cell
+    x.eliminate_zeros()
+    ad = sb.MiniAnnData(x.copy())
+    with pytest.warns(UserWarning, match="Some cells have zero counts"):
+        sb.pp.normalize_total(ad, key_added="nf")
+    ox, oc, _ = op.normalize_total(x)
+    np.testing.assert_allclose(ad.X.data, ox.data, rtol=1e-6)
+    np.testing.assert_allclose(ad.obs["nf"].to_numpy(), oc, rtol=1e-6)
+    sb.pp.log1p(ad, base=2)
+    np.testing.assert_allclose(ad.X.data, op.log1p(ox, base=2).data, rtol=2e-6)
+    with pytest.raises(ValueError, match="max_fraction between 0 and 1"):
+        sb.pp.normalize_total(ad, max_fraction=2)

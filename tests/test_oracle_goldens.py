@@ -120,3 +120,41 @@ def test_leiden_oracle_planted():
     m, q, _ = leiden.leiden(sparse.csr_matrix(a), seed=3)
     assert adjusted_rand_score(lab, m) == pytest.approx(1.0)
     assert q > 0.8
+
+
+# ---------------------------------------------------------------------------------------------------------
+# preprocessing oracle
+def _raw_pbmc():
+    from pathlib import Path
+
+    f = np.load(Path(__file__).parent / "golden" / "pbmc68k_raw_seurat_hvg.npz")
+    return sparse.csr_matrix((f["raw_data"], f["raw_indices"], f["raw_indptr"]), shape=(700, 765)), f
+
+
+def test_normalize_total_oracle_docstring_goldens():
+    from oracle import preprocess as op
+
+    # src/scanpy/preprocessing/_normalization.py:205-241 (docstring example)
+    a = np.array([[3, 3, 3, 6, 6], [1, 1, 1, 2, 2], [1, 22, 1, 2, 2]], dtype=np.float32)
+    x, _, _ = op.normalize_total(a, target_sum=1)
+    np.testing.assert_allclose(x.toarray(), [[1 / 7, 1 / 7, 1 / 7, 2 / 7, 2 / 7]] * 2 + [[1 / 28, 22 / 28, 1 / 28, 2 / 28, 2 / 28]], rtol=1e-6)
+    x, _, gs = op.normalize_total(a, target_sum=1, exclude_highly_expressed=True, max_fraction=0.2)
+    np.testing.assert_allclose(x.toarray(), [[0.5, 0.5, 0.5, 1, 1], [0.5, 0.5, 0.5, 1, 1], [0.5, 11, 0.5, 1, 1]], rtol=1e-6)
+    assert gs.tolist() == [True, False, True, False, False]
+    # tests/test_normalization.py:30-71
+    x, _, _ = op.normalize_total(np.array([[1, 0], [3, 0], [5, 6]]))
+    np.testing.assert_allclose(np.asarray(x.sum(axis=1)).ravel(), [3.0, 3.0, 3.0])
+    x, _, _ = op.normalize_total(np.array([[1, 0, 1], [3, 0, 1], [5, 6, 1]]), exclude_highly_expressed=True, max_fraction=0.7)
+    np.testing.assert_allclose(np.asarray(x[:, 1:3].sum(axis=1)).ravel(), [1.0, 1.0, 1.0])
+
+
+def test_hvg_seurat_oracle_matches_seurat_csv():
+    # tests/test_highly_variable_genes.py:379-421 (golden tests/_scripts/seurat_hvg.csv, rtol=atol=2e-5 there)
+    from oracle import preprocess as op
+
+    x, f = _raw_pbmc()
+    xn, _, _ = op.normalize_total(x, target_sum=1e4)
+    df = op.hvg_seurat(op.log1p(xn), min_mean=0.0125, max_mean=3, min_disp=0.5)
+    np.testing.assert_array_equal(df["highly_variable"].to_numpy(), f["highly_variable"])
+    for k in ("means", "dispersions", "dispersions_norm"):
+        np.testing.assert_allclose(df[k].to_numpy(), f[k], rtol=2e-5, atol=2e-5)
