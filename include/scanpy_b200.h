@@ -146,6 +146,12 @@ int32_t sb2_fuzzy_simplicial_set_f32(sb2_ctx* ctx, int64_t n, int32_t k, const i
                                      int64_t* d_indptr, int32_t* d_indices, float* d_data, int64_t cap,
                                      int64_t* h_nnz, float* d_sigmas, float* d_rhos);
 
+/* method='gauss' (method 1) / 'jaccard' (method 2) connectivities from the same k-lists (SURVEY.md 8f row f3;
+ * src/scanpy/neighbors/_connectivity.py:17-100 sparse kNN branch, :141-186).  float64 values like the reference. */
+int32_t sb2_knn_connectivities_f64(sb2_ctx* ctx, int64_t n, int32_t k, const int32_t* d_knn_idx, const double* d_knn_dist,
+                                   int32_t method, int64_t* d_indptr, int32_t* d_indices, double* d_data, int64_t cap,
+                                   int64_t* h_nnz);
+
 /* ---- Leiden on a symmetric weighted CSR graph ------------------------------------------------
  * n_iterations < 0: iterate until a whole pass moves nothing.  Output membership int32[n]
  * renumbered by decreasing community size; *h_modularity at the given resolution. */

@@ -73,6 +73,8 @@ SIGNATURES = {
     "sb2_fuzzy_simplicial_set_f32": (c_int32, [c_void_p, c_int64, c_int32, c_void_p, c_void_p, c_float, c_float,
                                                c_void_p, c_void_p, c_void_p, c_int64, POINTER(c_int64), c_void_p,
                                                c_void_p]),
+    "sb2_knn_connectivities_f64": (c_int32, [c_void_p, c_int64, c_int32, c_void_p, c_void_p, c_int32, c_void_p, c_void_p,
+                                             c_void_p, c_int64, POINTER(c_int64)]),
     "sb2_leiden_csr_f32": (c_int32, [c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_double, c_int32, c_uint64,
                                      c_void_p, POINTER(c_double), POINTER(c_int32), POINTER(LeidenInfo)]),
     "sb2_modularity_csr_f32": (c_int32, [c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_double, c_void_p,

@@ -148,6 +148,27 @@ def fuzzy_simplicial_set(knn_indices: np.ndarray, knn_dists: np.ndarray, *, ctx=
     return c, h_sig, h_rho
 
 
+def knn_connectivities(knn_indices: np.ndarray, knn_dists: np.ndarray, method: str, *, ctx=None):
+    """method='gauss' | 'jaccard' connectivities from k-lists -> scipy CSR float64 (sorted, no explicit zeros)."""
+    from scipy import sparse
+
+    torch = _torch()
+    ctx = ctx or _abi.default_context()
+    n, k = knn_indices.shape
+    d_idx = _to_device(np.asarray(knn_indices, dtype=np.int32))
+    d_dist = _to_device(np.asarray(knn_dists, dtype=np.float64))
+    cap = 2 * n * max(k - 1, 1)
+    indptr = torch.empty(n + 1, dtype=torch.int64, device="cuda")
+    indices = torch.empty(cap, dtype=torch.int32, device="cuda")
+    data = torch.empty(cap, dtype=torch.float64, device="cuda")
+    nnz = c_int64()
+    check(ctx.lib.sb2_knn_connectivities_f64(ctx.handle, n, k, ptr(d_idx), ptr(d_dist), {"gauss": 1, "jaccard": 2}[method],
+                                             ptr(indptr), ptr(indices), ptr(data), cap, byref(nnz)))
+    m = nnz.value
+    ip, h_data, h_indices = _to_host(indptr, data[:m].contiguous(), indices[:m].contiguous())
+    return sparse.csr_matrix((h_data, h_indices, ip if ip[-1] >= 2**31 else ip.astype(np.int32)), shape=(n, n))
+
+
 def knn_and_connectivities(x: np.ndarray, n_neighbors: int, *, ctx=None):
     """Exact kNN + UMAP connectivities with the (idx, dist) lists kept on the device in between.
     -> (indices int32 [n,k], distances float64 [n,k], connectivities scipy CSR float32)."""

@@ -119,52 +119,59 @@ fuzzy_rows_kernel(int64_t n, int k, const int32_t* __restrict__ knn_idx, const d
   }
 }
 
-__device__ __forceinline__ float fuzzy_union(float a, float b, float mix) {
-  const float p = a * b;
-  return mix * (a + b - p) + (1.0f - mix) * p;
+// how the directed weight a = W[i,j] and its reverse b = W[j,i] (0 if absent) combine into C[i,j] = C[j,i]
+enum SymOp { SYM_FUZZY_UNION = 0, SYM_AVERAGE = 1, SYM_COPY_MISSING = 2 };
+template <typename T>
+__device__ __forceinline__ T sym_combine(T a, T b, int op, T mix) {
+  if (op == SYM_AVERAGE) return (a + b) / (T)2;         // jaccard: (J + J^T) / 2   (_connectivity.py:183-184)
+  if (op == SYM_COPY_MISSING) return a != (T)0 ? a : b;  // gauss: w[j,i] = w[i,j] where missing (:93-97)
+  const T p = a * b;                                     // umap: mix (a + b - ab) + (1 - mix) ab
+  return mix * (a + b - p) + ((T)1 - mix) * p;
 }
 
 // one thread per (i, m): value of C[i, idx[i][m]] and in-only bookkeeping
-__global__ void sym_count_kernel(int64_t n, int k, const int32_t* __restrict__ knn_idx, const float* __restrict__ w,
-                                 float mix, float* __restrict__ cval, uint8_t* __restrict__ inonly,
+template <typename T>
+__global__ void sym_count_kernel(int64_t n, int k, const int32_t* __restrict__ knn_idx, const T* __restrict__ w,
+                                 int op, T mix, T* __restrict__ cval, uint8_t* __restrict__ inonly,
                                  int32_t* __restrict__ n_out, int32_t* __restrict__ n_in) {
   const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= n * k) return;
   const int64_t i = t / k;
   const int32_t j = knn_idx[t];
-  float c = 0.0f;
+  T c = (T)0;
   bool in_only = false;
   if (j >= 0 && j != (int32_t)i) {
-    const float a = w[t];
-    float b = 0.0f;
+    const T a = w[t];
+    T b = (T)0;
     bool found = false;
     const int32_t* lj = knn_idx + (int64_t)j * k;
     for (int m = 0; m < k; ++m) {
       if (lj[m] == (int32_t)i) { found = true; b = w[(int64_t)j * k + m]; break; }
     }
-    c = fuzzy_union(a, b, mix);
-    in_only = !found && c != 0.0f;
+    c = sym_combine<T>(a, b, op, mix);
+    in_only = !found && c != (T)0;
   }
   cval[t] = c;
   inonly[t] = in_only ? 1 : 0;
-  if (c != 0.0f) atomicAdd(&n_out[i], 1);
+  if (c != (T)0) atomicAdd(&n_out[i], 1);
   if (in_only) atomicAdd(&n_in[j], 1);
 }
 __global__ void add_i32_kernel(const int32_t* __restrict__ a, const int32_t* __restrict__ b, int32_t* __restrict__ c, int64_t n) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) c[i] = a[i] + b[i];
 }
-__global__ void sym_fill_kernel(int64_t n, int k, const int32_t* __restrict__ knn_idx, const float* __restrict__ cval,
+template <typename T>
+__global__ void sym_fill_kernel(int64_t n, int k, const int32_t* __restrict__ knn_idx, const T* __restrict__ cval,
                                 const uint8_t* __restrict__ inonly, const int64_t* __restrict__ indptr,
                                 const int32_t* __restrict__ n_out, int32_t* __restrict__ cursor,
-                                int32_t* __restrict__ t_indices, float* __restrict__ t_data) {
+                                int32_t* __restrict__ t_indices, T* __restrict__ t_data) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   int64_t p = indptr[i];
   for (int m = 0; m < k; ++m) {
     const int64_t t = i * k + m;
-    const float c = cval[t];
-    if (c != 0.0f) {
+    const T c = cval[t];
+    if (c != (T)0) {
       t_indices[p] = knn_idx[t];
       t_data[p] = c;
       ++p;
@@ -177,9 +184,10 @@ __global__ void sym_fill_kernel(int64_t n, int k, const int32_t* __restrict__ kn
     }
   }
 }
+template <typename T>
 __global__ void __launch_bounds__(256)
 sym_sort_rows_kernel(int64_t n, const int64_t* __restrict__ indptr, const int32_t* __restrict__ t_indices,
-                     const float* __restrict__ t_data, int32_t* __restrict__ indices, float* __restrict__ data) {
+                     const T* __restrict__ t_data, int32_t* __restrict__ indices, T* __restrict__ data) {
   const int lane = threadIdx.x & 31;
   const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= n) return;
@@ -187,13 +195,13 @@ sym_sort_rows_kernel(int64_t n, const int64_t* __restrict__ indptr, const int32_
   const int len = (int)(indptr[row + 1] - p0);
   if (len <= 32) {
     int32_t key = lane < len ? t_indices[p0 + lane] : INT32_MAX;
-    float val = lane < len ? t_data[p0 + lane] : 0.0f;
+    T val = lane < len ? t_data[p0 + lane] : (T)0;
 #pragma unroll
     for (int kk = 2; kk <= 32; kk <<= 1) {
 #pragma unroll
       for (int j = kk >> 1; j > 0; j >>= 1) {
         const int32_t ok = __shfl_xor_sync(0xffffffffu, key, j);
-        const float ov = __shfl_xor_sync(0xffffffffu, val, j);
+        const T ov = __shfl_xor_sync(0xffffffffu, val, j);
         const bool want_min = ((lane & j) == 0) == ((lane & kk) == 0);
         const bool take = want_min ? (ok < key) : (ok > key);
         if (take) { key = ok; val = ov; }
@@ -211,41 +219,74 @@ sym_sort_rows_kernel(int64_t n, const int64_t* __restrict__ indptr, const int32_
   }
 }
 
-}  // namespace
+// ---- method='jaccard' / 'gauss' directed weights, fp64 like the reference ----
+// jaccard (src/scanpy/neighbors/_connectivity.py:141-186): |N(i) & N(j)| / (2(k-1) - |N(i) & N(j)|), self excluded
+__global__ void jaccard_rows_kernel(int64_t n, int k, const int32_t* __restrict__ knn_idx, double* __restrict__ w) {
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n * k) return;
+  const int64_t i = t / k;
+  const int m = (int)(t % k);
+  const int32_t j = knn_idx[t];
+  double val = 0.0;
+  if (m > 0 && j >= 0 && j != (int32_t)i) {
+    const int32_t* li = knn_idx + i * k;
+    const int32_t* lj = knn_idx + (int64_t)j * k;
+    int shared = 0;
+    for (int a = 1; a < k; ++a) {
+      const int32_t x = li[a];
+      for (int b = 1; b < k; ++b) shared += (lj[b] == x);
+    }
+    val = (double)shared / (double)(2 * (k - 1) - shared);
+  }
+  w[t] = val;
+}
+// gauss, sparse kNN branch (:17-100): sigma_i^2 = median of the k-1 squared neighbour distances
+__global__ void gauss_sigma_kernel(int64_t n, int k, const double* __restrict__ knn_dist, double* __restrict__ sig_sq) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double d[MAXK];
+  const int m = k - 1;
+  for (int j = 0; j < m; ++j) { const double x = knn_dist[i * k + 1 + j]; d[j] = x * x; }
+  for (int a = 1; a < m; ++a) {  // insertion sort (rows arrive ascending already)
+    const double x = d[a];
+    int b = a - 1;
+    while (b >= 0 && d[b] > x) { d[b + 1] = d[b]; --b; }
+    d[b + 1] = x;
+  }
+  sig_sq[i] = (m & 1) ? d[m / 2] : 0.5 * (d[m / 2 - 1] + d[m / 2]);  // np.median
+}
+__global__ void gauss_rows_kernel(int64_t n, int k, const int32_t* __restrict__ knn_idx, const double* __restrict__ knn_dist,
+                                  const double* __restrict__ sig_sq, double* __restrict__ w) {
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n * k) return;
+  const int64_t i = t / k;
+  const int m = (int)(t % k);
+  const int32_t j = knn_idx[t];
+  double val = 0.0;
+  if (m > 0 && j >= 0 && j != (int32_t)i) {
+    const double si2 = sig_sq[i], sj2 = sig_sq[j];
+    const double num = 2.0 * sqrt(si2) * sqrt(sj2), den = si2 + sj2;
+    const double d = knn_dist[t];
+    val = sqrt(num / den) * exp(-(d * d) / den);
+  }
+  w[t] = val;
+}
 
-extern "C" int32_t sb2_fuzzy_simplicial_set_f32(sb2_ctx* ctx, int64_t n, int32_t k, const int32_t* d_knn_idx,
-                                                const double* d_knn_dist, float set_op_mix_ratio,
-                                                float local_connectivity, int64_t* d_indptr, int32_t* d_indices,
-                                                float* d_data, int64_t cap, int64_t* h_nnz, float* d_sigmas,
-                                                float* d_rhos) {
-  SB2_CHECK_ARG(ctx && d_knn_idx && d_knn_dist && d_indptr && d_indices && d_data && h_nnz, "null pointer");
-  SB2_CHECK_ARG(n >= 1 && k >= 2 && k <= MAXK, "k must be in [2,32]");
-  SB2_CHECK_ARG(set_op_mix_ratio >= 0.0f && set_op_mix_ratio <= 1.0f, "set_op_mix_ratio in [0,1]");
-  SB2_CHECK_ARG(local_connectivity >= 0.0f && local_connectivity < (float)k, "local_connectivity");
-  SB2_CUDA(cudaSetDevice(ctx->device));
+// directed k-list weights w[n x k] -> symmetric CSR (sorted rows, no explicit zeros); syncs the stream
+template <typename T>
+int32_t symmetrize(sb2_ctx* ctx, ScratchScope& scr, int64_t n, int32_t k, const int32_t* d_knn_idx, const T* w, int op, T mix,
+                   int64_t* d_indptr, int32_t* d_indices, T* d_data, int64_t cap, int64_t* h_nnz) {
   cudaStream_t st = ctx->stream;
-  ScratchScope scr(ctx);
   const int64_t nk = n * k;
-  float *w, *cval, *t_data, *sig, *rho;
+  T *cval, *t_data;
   uint8_t* inonly;
   int32_t *n_out, *n_in, *len, *cursor, *t_indices;
-  double* dsum;
-  SB2_TRY(scr.alloc(&w, (size_t)nk));
   SB2_TRY(scr.alloc(&cval, (size_t)nk));
   SB2_TRY(scr.alloc(&inonly, (size_t)nk));
   SB2_TRY(scr.alloc(&n_out, (size_t)n * 4));
   n_in = n_out + n; len = n_in + n; cursor = len + n;
-  SB2_TRY(scr.alloc(&dsum, 2));
-  SB2_TRY(scr.alloc(&sig, (size_t)n));
-  SB2_TRY(scr.alloc(&rho, (size_t)n));
   SB2_CUDA(cudaMemsetAsync(n_out, 0, sizeof(int32_t) * 4 * n, st));
-  SB2_CUDA(cudaMemsetAsync(dsum, 0, 16, st));
-  sum_f32cast_kernel<<<ctx->prop.multiProcessorCount * 4, 256, 0, st>>>(d_knn_dist, nk, dsum);
-  SB2_LAUNCH_CHECK(ctx);
-  fuzzy_rows_kernel<<<(unsigned)ceil_div64(n, 128), 128, 0, st>>>(n, k, d_knn_idx, d_knn_dist, local_connectivity, dsum, w,
-                                                                 d_sigmas ? d_sigmas : sig, d_rhos ? d_rhos : rho);
-  SB2_LAUNCH_CHECK(ctx);
-  sym_count_kernel<<<(unsigned)ceil_div64(nk, 256), 256, 0, st>>>(n, k, d_knn_idx, w, set_op_mix_ratio, cval, inonly, n_out, n_in);
+  sym_count_kernel<T><<<(unsigned)ceil_div64(nk, 256), 256, 0, st>>>(n, k, d_knn_idx, w, op, mix, cval, inonly, n_out, n_in);
   SB2_LAUNCH_CHECK(ctx);
   add_i32_kernel<<<(unsigned)ceil_div64(n, 256), 256, 0, st>>>(n_out, n_in, len, n);
   SB2_LAUNCH_CHECK(ctx);
@@ -260,10 +301,69 @@ extern "C" int32_t sb2_fuzzy_simplicial_set_f32(sb2_ctx* ctx, int64_t n, int32_t
   }
   SB2_TRY(scr.alloc(&t_indices, (size_t)nnz));
   SB2_TRY(scr.alloc(&t_data, (size_t)nnz));
-  sym_fill_kernel<<<(unsigned)ceil_div64(n, 128), 128, 0, st>>>(n, k, d_knn_idx, cval, inonly, d_indptr, n_out, cursor, t_indices, t_data);
+  sym_fill_kernel<T><<<(unsigned)ceil_div64(n, 128), 128, 0, st>>>(n, k, d_knn_idx, cval, inonly, d_indptr, n_out, cursor, t_indices, t_data);
   SB2_LAUNCH_CHECK(ctx);
-  sym_sort_rows_kernel<<<(unsigned)ceil_div64(n, 8), 256, 0, st>>>(n, d_indptr, t_indices, t_data, d_indices, d_data);
+  sym_sort_rows_kernel<T><<<(unsigned)ceil_div64(n, 8), 256, 0, st>>>(n, d_indptr, t_indices, t_data, d_indices, d_data);
   SB2_LAUNCH_CHECK(ctx);
   SB2_CUDA(cudaStreamSynchronize(st));
   return SB2_OK;
 }
+
+}  // namespace
+
+extern "C" int32_t sb2_knn_connectivities_f64(sb2_ctx* ctx, int64_t n, int32_t k, const int32_t* d_knn_idx,
+                                              const double* d_knn_dist, int32_t method, int64_t* d_indptr,
+                                              int32_t* d_indices, double* d_data, int64_t cap, int64_t* h_nnz) {
+  SB2_CHECK_ARG(ctx && d_knn_idx && d_indptr && d_indices && d_data && h_nnz, "null pointer");
+  SB2_CHECK_ARG(n >= 1 && k >= 2 && k <= MAXK, "k must be in [2,32]");
+  SB2_CHECK_ARG(method == 1 || method == 2, "method: 1 = gauss, 2 = jaccard");
+  SB2_CHECK_ARG(method == 2 || d_knn_dist, "gauss needs distances");
+  SB2_CUDA(cudaSetDevice(ctx->device));
+  cudaStream_t st = ctx->stream;
+  ScratchScope scr(ctx);
+  const int64_t nk = n * k;
+  double* w;
+  SB2_TRY(scr.alloc(&w, (size_t)nk));
+  if (method == 2) {
+    jaccard_rows_kernel<<<(unsigned)ceil_div64(nk, 256), 256, 0, st>>>(n, k, d_knn_idx, w);
+    SB2_LAUNCH_CHECK(ctx);
+    return symmetrize<double>(ctx, scr, n, k, d_knn_idx, w, SYM_AVERAGE, 1.0, d_indptr, d_indices, d_data, cap, h_nnz);
+  }
+  double* sig_sq;
+  SB2_TRY(scr.alloc(&sig_sq, (size_t)n));
+  gauss_sigma_kernel<<<(unsigned)ceil_div64(n, 128), 128, 0, st>>>(n, k, d_knn_dist, sig_sq);
+  SB2_LAUNCH_CHECK(ctx);
+  gauss_rows_kernel<<<(unsigned)ceil_div64(nk, 256), 256, 0, st>>>(n, k, d_knn_idx, d_knn_dist, sig_sq, w);
+  SB2_LAUNCH_CHECK(ctx);
+  return symmetrize<double>(ctx, scr, n, k, d_knn_idx, w, SYM_COPY_MISSING, 1.0, d_indptr, d_indices, d_data, cap, h_nnz);
+}
+
+extern "C" int32_t sb2_fuzzy_simplicial_set_f32(sb2_ctx* ctx, int64_t n, int32_t k, const int32_t* d_knn_idx,
+                                                const double* d_knn_dist, float set_op_mix_ratio,
+                                                float local_connectivity, int64_t* d_indptr, int32_t* d_indices,
+                                                float* d_data, int64_t cap, int64_t* h_nnz, float* d_sigmas,
+                                                float* d_rhos) {
+  SB2_CHECK_ARG(ctx && d_knn_idx && d_knn_dist && d_indptr && d_indices && d_data && h_nnz, "null pointer");
+  SB2_CHECK_ARG(n >= 1 && k >= 2 && k <= MAXK, "k must be in [2,32]");
+  SB2_CHECK_ARG(set_op_mix_ratio >= 0.0f && set_op_mix_ratio <= 1.0f, "set_op_mix_ratio in [0,1]");
+  SB2_CHECK_ARG(local_connectivity >= 0.0f && local_connectivity < (float)k, "local_connectivity");
+  SB2_CUDA(cudaSetDevice(ctx->device));
+  cudaStream_t st = ctx->stream;
+  ScratchScope scr(ctx);
+  const int64_t nk = n * k;
+  float *w, *sig, *rho;
+  double* dsum;
+  SB2_TRY(scr.alloc(&w, (size_t)nk));
+  SB2_TRY(scr.alloc(&dsum, 2));
+  SB2_TRY(scr.alloc(&sig, (size_t)n));
+  SB2_TRY(scr.alloc(&rho, (size_t)n));
+  SB2_CUDA(cudaMemsetAsync(dsum, 0, 16, st));
+  sum_f32cast_kernel<<<ctx->prop.multiProcessorCount * 4, 256, 0, st>>>(d_knn_dist, nk, dsum);
+  SB2_LAUNCH_CHECK(ctx);
+  fuzzy_rows_kernel<<<(unsigned)ceil_div64(n, 128), 128, 0, st>>>(n, k, d_knn_idx, d_knn_dist, local_connectivity, dsum, w,
+                                                                 d_sigmas ? d_sigmas : sig, d_rhos ? d_rhos : rho);
+  SB2_LAUNCH_CHECK(ctx);
+  return symmetrize<float>(ctx, scr, n, k, d_knn_idx, w, SYM_FUZZY_UNION, set_op_mix_ratio, d_indptr, d_indices, d_data, cap,
+                           h_nnz);
+}
+

@@ -277,8 +277,6 @@ def neighbors(adata, n_neighbors: int = 15, n_pcs: int | None = None, *, distanc
     meta_rs = meta_random_state(rng)
     if method not in ("umap", "gauss", "jaccard") and method is not None:
         raise ValueError("`method` needs to be one of ('umap', 'gauss', 'jaccard').")
-    if method in ("gauss", "jaccard"):
-        raise NotImplementedError(f"method={method!r} connectivities are not implemented in scanpy_b200.")
     if distances is not None:
         return _neighbors_from_distances(adata, n_neighbors, distances=distances, method=method, metric=metric,
                                          metric_kwds=metric_kwds, use_rep=use_rep, n_pcs=n_pcs, knn=knn,
@@ -303,7 +301,7 @@ def neighbors(adata, n_neighbors: int = 15, n_pcs: int | None = None, *, distanc
         n_neighbors = 1 + int(0.5 * adata.shape[0])
         warn(f"n_obs too small: adjusting to `n_neighbors = {n_neighbors}`", UserWarning)
     x = _choose_representation(adata, use_rep=use_rep, n_pcs=n_pcs)
-    if transformer is None or isinstance(transformer, str):
+    if (transformer is None or isinstance(transformer, str)) and method == "umap":
         # built-in exact kNN: (idx, dist) stay in HBM between the search and the fuzzy-set kernels, so the
         # n x k lists cross PCIe once (device -> host) instead of three times
         xd = x.toarray() if sparse.issparse(x) else np.asarray(x)
@@ -312,9 +310,14 @@ def neighbors(adata, n_neighbors: int = 15, n_pcs: int | None = None, *, distanc
         if knn_indices.shape[1] > n_neighbors:
             knn_indices, knn_distances = knn_indices[:, :n_neighbors], knn_distances[:, :n_neighbors]
     else:
+        if transformer is None or isinstance(transformer, str):
+            transformer = B200KNNTransformer(n_neighbors=n_neighbors, metric=metric)
         d = transformer.fit_transform(x)
         knn_indices, knn_distances = _get_indices_distances_from_sparse_matrix(d, n_neighbors)
-        conn, _, _ = _ops.fuzzy_simplicial_set(knn_indices, knn_distances)
+        if method == "umap":
+            conn, _, _ = _ops.fuzzy_simplicial_set(knn_indices, knn_distances)
+        else:  # 'gauss' | 'jaccard' (src/scanpy/neighbors/__init__.py:675-701)
+            conn = _ops.knn_connectivities(knn_indices, knn_distances, method)
     dist_csr = _get_sparse_matrix_from_indices_distances(knn_indices, knn_distances, keep_self=False)
 
     if key_added is None:

@@ -97,14 +97,17 @@ def main() -> None:
     pca_l = literals_from(REF / "tests/test_pca.py", {"A_list", "A_pca", "A_svd"})
     nb_l = literals_from(
         REF / "tests/test_neighbors.py",
-        {"X", "n_neighbors", "distances_euclidean", "distances_euclidean_all", "connectivities_umap"},
+        {"X", "n_neighbors", "distances_euclidean", "distances_euclidean_all", "connectivities_umap",
+         "connectivities_gauss_knn", "connectivities_jaccard"},
     )
     np.savez(OUT / "reference_test_literals.npz",
              A_list=pca_l["A_list"].astype(np.float64), A_pca=pca_l["A_pca"], A_svd=pca_l["A_svd"],
              X4=nb_l["X"].astype(np.float64), n_neighbors4=np.int64(nb_l["n_neighbors"]),
              distances_euclidean=nb_l["distances_euclidean"],
              distances_euclidean_all=nb_l["distances_euclidean_all"],
-             connectivities_umap=nb_l["connectivities_umap"])
+             connectivities_umap=nb_l["connectivities_umap"],
+             connectivities_gauss_knn=nb_l["connectivities_gauss_knn"],
+             connectivities_jaccard=nb_l["connectivities_jaccard"])
 
     z = zipfile.ZipFile(REF / "src/scanpy/datasets/10x_pbmc68k_reduced.zarr.zip")
     fx = {

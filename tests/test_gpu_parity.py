@@ -370,3 +370,27 @@ def test_normalize_total_and_log1p_match_oracle():
     np.testing.assert_allclose(ad.X.data, op.log1p(ox, base=2).data, rtol=2e-6)
     with pytest.raises(ValueError, match="max_fraction between 0 and 1"):
         sb.pp.normalize_total(ad, max_fraction=2)
+
+
+# ------------------------------------------------------------------------------------------ gauss / jaccard (8f, f3)
+def test_gauss_jaccard_goldens_and_oracle(literals):
+    from oracle import connectivity as oconn
+
+    # reference 4-point goldens: tests/test_neighbors.py:66-72,120-126,195-226
+    ad = sb.MiniAnnData(literals["X4"].astype(np.float32))
+    for method, key in (("gauss", "connectivities_gauss_knn"), ("jaccard", "connectivities_jaccard")):
+        sb.pp.neighbors(ad, n_neighbors=int(literals["n_neighbors4"]), method=method, key_added=method)
+        c = ad.obsp[f"{method}_connectivities"]
+        assert c.dtype == np.float64 and ad.uns[method]["params"]["method"] == method
+        np.testing.assert_allclose(c.toarray(), literals[key], rtol=1e-6, atol=1e-7)
+    rs = np.random.RandomState(1)
+    x = rs.standard_normal((3000, 12)).astype(np.float32)
+    x[:1000] += 3
+    idx, dist, _ = _ops.knn(x, 15)
+    for method, ofun in (("gauss", lambda: oconn.gauss_knn(idx, dist)), ("jaccard", lambda: oconn.jaccard(idx))):
+        c = _ops.knn_connectivities(idx, dist, method)
+        o = ofun().tocsr()
+        o.sort_indices(); o.eliminate_zeros()
+        assert c.has_sorted_indices and c.nnz == o.nnz and (c.indices == o.indices).all()
+        np.testing.assert_allclose(c.data, o.data, rtol=1e-12, atol=1e-300)
+        assert abs(c - c.T).max() < 1e-15

@@ -128,8 +128,6 @@ def test_neighbors_and_leiden_argument_errors_match_reference():
         pp.neighbors(a, knn=False)  # :748-751
     with pytest.raises(ValueError, match="Unknown transformer: nope"):
         pp.neighbors(a, transformer="nope")  # :782-787
-    with pytest.raises(NotImplementedError, match="gauss"):
-        pp.neighbors(a, method="gauss")
     with pytest.raises(ValueError, match="Did not find X_foo"):
         pp._choose_representation(a, use_rep="X_foo", n_pcs=None)  # tools/_utils.py:48-50
     # tests/test_clustering.py:105-127
