@@ -314,6 +314,38 @@ agg_fill_kernel(int32_t nc, const int64_t* __restrict__ slice, const int32_t* __
     out += __popc(m);
   }
 }
+// block-per-super-vertex variants for coarse levels (few super-vertices with very long hash slices)
+__global__ void __launch_bounds__(256)
+agg_count_block_kernel(int32_t nc, const int64_t* __restrict__ slice, const int32_t* __restrict__ hkeys,
+                       int32_t* __restrict__ cnt) {
+  __shared__ int total;
+  const int32_t r = blockIdx.x;
+  if (threadIdx.x == 0) total = 0;
+  __syncthreads();
+  int c = 0;
+  for (int64_t s = slice[r] + threadIdx.x; s < slice[r + 1]; s += blockDim.x) c += hkeys[s] >= 0;
+  for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+  if ((threadIdx.x & 31) == 0 && c) atomicAdd(&total, c);
+  __syncthreads();
+  if (threadIdx.x == 0) cnt[r] = total;
+}
+__global__ void __launch_bounds__(256)
+agg_fill_block_kernel(int32_t nc, const int64_t* __restrict__ slice, const int32_t* __restrict__ hkeys,
+                      const int64_t* __restrict__ hvals, const int64_t* __restrict__ indptr_new,
+                      int32_t* __restrict__ indices_new, int64_t* __restrict__ w_new) {
+  __shared__ int cursor;  // entry order inside a row is irrelevant (all reductions are exact integers)
+  const int32_t r = blockIdx.x;
+  if (threadIdx.x == 0) cursor = 0;
+  __syncthreads();
+  const int64_t out = indptr_new[r];
+  for (int64_t s = slice[r] + threadIdx.x; s < slice[r + 1]; s += blockDim.x) {
+    if (hkeys[s] >= 0) {
+      const int p = atomicAdd(&cursor, 1);
+      indices_new[out + p] = hkeys[s];
+      w_new[out + p] = hvals[s];
+    }
+  }
+}
 __global__ void compose_kernel(int64_t n0, int32_t* __restrict__ node_of, const int32_t* __restrict__ rnew) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n0) node_of[i] = rnew[node_of[i]];
@@ -451,7 +483,7 @@ int32_t refine(Work& w, const Level& L, const int32_t* comm, int32_t* ref, int64
 // quality of `comm` (labels < n) on the level-0 fixed-point graph; K/csize scratch sized n
 static int32_t quality_device(sb2_ctx* ctx, ScratchScope& scr, int32_t n, const int64_t* indptr, const int32_t* indices,
                               const int64_t* wfx, const int64_t* kfx, double total, double gamma, const int32_t* comm,
-                              double* q_out) {
+                              double* q_out, int32_t n_labels = -1) {
   cudaStream_t st = ctx->stream;
   u64* K;
   int32_t* csize;
@@ -466,14 +498,15 @@ static int32_t quality_device(sb2_ctx* ctx, ScratchScope& scr, int32_t n, const 
   SB2_LAUNCH_CHECK(ctx);
   internal_weight_kernel<<<gridt(n), 256, 0, st>>>(n, indptr, indices, wfx, comm, internal);
   SB2_LAUNCH_CHECK(ctx);
-  std::vector<u64> hK((size_t)n);
+  const int32_t nl = (n_labels > 0 && n_labels < n) ? n_labels : n;  // labels are < nl (compact after renumbering)
+  std::vector<u64> hK((size_t)nl);
   u64 hin = 0;
-  SB2_CUDA(cudaMemcpyAsync(hK.data(), K, sizeof(u64) * n, cudaMemcpyDeviceToHost, st));
+  SB2_CUDA(cudaMemcpyAsync(hK.data(), K, sizeof(u64) * nl, cudaMemcpyDeviceToHost, st));
   SB2_CUDA(cudaMemcpyAsync(&hin, internal, sizeof(u64), cudaMemcpyDeviceToHost, st));
   SB2_CUDA(cudaStreamSynchronize(st));
   if (total <= 0.0) { *q_out = 0.0; return SB2_OK; }
   double pen = 0.0;
-  for (int32_t c = 0; c < n; ++c) {
+  for (int32_t c = 0; c < nl; ++c) {
     const double kc = (double)(long long)hK[c];
     pen += kc * kc;
   }
@@ -481,35 +514,74 @@ static int32_t quality_device(sb2_ctx* ctx, ScratchScope& scr, int32_t n, const 
   return SB2_OK;
 }
 
-// renumber labels (< n) by decreasing size, ties -> smaller first member; returns #communities
+// renumber labels (< n) by decreasing size, ties -> smaller first member; returns #communities.
+// Sizes / first members are gathered with integer atomics, only the (few) non-empty labels travel to the host
+// for the sort.
+namespace {
+__global__ void label_stats_kernel(int64_t n, const int32_t* __restrict__ comm, int32_t* __restrict__ csize,
+                                   int32_t* __restrict__ minmem) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  atomicAdd(&csize[comm[i]], 1);
+  atomicMin(&minmem[comm[i]], (int32_t)i);
+}
+__global__ void label_compact_kernel(int64_t n, const int32_t* __restrict__ csize, const int32_t* __restrict__ minmem,
+                                     const int64_t* __restrict__ pos, int32_t* __restrict__ lab, int32_t* __restrict__ sz,
+                                     int32_t* __restrict__ mm) {
+  const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= n || csize[c] <= 0) return;
+  const int64_t p = pos[c];
+  lab[p] = (int32_t)c; sz[p] = csize[c]; mm[p] = minmem[c];
+}
+__global__ void label_scatter_kernel(int32_t nc, const int32_t* __restrict__ lab, const int32_t* __restrict__ rank,
+                                     int32_t* __restrict__ newid) {
+  const int32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p < nc) newid[lab[p]] = rank[p];
+}
+}  // namespace
 static int32_t renumber_device(sb2_ctx* ctx, ScratchScope& scr, int64_t n, int32_t* comm, int32_t* n_comms) {
   cudaStream_t st = ctx->stream;
-  int32_t *minmem, *newid;
+  int32_t *csize, *minmem, *newid, *flag, *lab, *sz, *mm, *rank;
+  int64_t* pos;
+  SB2_TRY(scr.alloc(&csize, (size_t)n));
   SB2_TRY(scr.alloc(&minmem, (size_t)n));
   SB2_TRY(scr.alloc(&newid, (size_t)n));
+  SB2_TRY(scr.alloc(&flag, (size_t)n));
+  SB2_TRY(scr.alloc(&pos, (size_t)n + 1));
+  SB2_CUDA(cudaMemsetAsync(csize, 0, sizeof(int32_t) * n, st));
   SB2_CUDA(cudaMemsetAsync(minmem, 0x7f, sizeof(int32_t) * n, st));
-  comm_min_member_kernel<<<gridt(n), 256, 0, st>>>(n, comm, minmem);
+  label_stats_kernel<<<gridt(n), 256, 0, st>>>(n, comm, csize, minmem);
   SB2_LAUNCH_CHECK(ctx);
-  std::vector<int32_t> hcomm((size_t)n), hmin((size_t)n);
-  SB2_CUDA(cudaMemcpyAsync(hcomm.data(), comm, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, st));
-  SB2_CUDA(cudaMemcpyAsync(hmin.data(), minmem, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, st));
+  flag_nonempty_kernel<<<gridt(n), 256, 0, st>>>((int32_t)n, csize, flag);
+  SB2_LAUNCH_CHECK(ctx);
+  SB2_TRY(sb2_scan_i32_to_i64(ctx, flag, n, pos));
+  int64_t nc64 = 0;
+  SB2_CUDA(cudaMemcpyAsync(&nc64, pos + n, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
   SB2_CUDA(cudaStreamSynchronize(st));
-  std::vector<int64_t> size((size_t)n, 0);
-  for (int64_t i = 0; i < n; ++i) size[hcomm[i]]++;
-  std::vector<int32_t> ids;
-  for (int64_t c = 0; c < n; ++c)
-    if (size[c] > 0) ids.push_back((int32_t)c);
-  std::sort(ids.begin(), ids.end(), [&](int32_t a, int32_t b) {
-    if (size[a] != size[b]) return size[a] > size[b];
-    return hmin[a] < hmin[b];
+  const int32_t nc = (int32_t)nc64;
+  SB2_TRY(scr.alloc(&lab, (size_t)nc * 4));
+  sz = lab + nc; mm = sz + nc; rank = mm + nc;
+  label_compact_kernel<<<gridt(n), 256, 0, st>>>(n, csize, minmem, pos, lab, sz, mm);
+  SB2_LAUNCH_CHECK(ctx);
+  std::vector<int32_t> h((size_t)nc * 3);
+  SB2_CUDA(cudaMemcpyAsync(h.data(), lab, sizeof(int32_t) * (size_t)nc * 3, cudaMemcpyDeviceToHost, st));
+  SB2_CUDA(cudaStreamSynchronize(st));
+  const int32_t* hsz = h.data() + nc;
+  const int32_t* hmm = h.data() + 2 * (size_t)nc;
+  std::vector<int32_t> ord((size_t)nc), hrank((size_t)nc);
+  for (int32_t p = 0; p < nc; ++p) ord[p] = p;
+  std::sort(ord.begin(), ord.end(), [&](int32_t a, int32_t b) {
+    if (hsz[a] != hsz[b]) return hsz[a] > hsz[b];
+    return hmm[a] < hmm[b];
   });
-  std::vector<int32_t> hnew((size_t)n, -1);
-  for (size_t r = 0; r < ids.size(); ++r) hnew[ids[r]] = (int32_t)r;
-  SB2_CUDA(cudaMemcpyAsync(newid, hnew.data(), sizeof(int32_t) * n, cudaMemcpyHostToDevice, st));
+  for (int32_t r = 0; r < nc; ++r) hrank[ord[r]] = r;
+  SB2_CUDA(cudaMemcpyAsync(rank, hrank.data(), sizeof(int32_t) * (size_t)nc, cudaMemcpyHostToDevice, st));
+  label_scatter_kernel<<<gridt(nc), 256, 0, st>>>(nc, lab, rank, newid);
+  SB2_LAUNCH_CHECK(ctx);
   relabel_kernel<<<gridt(n), 256, 0, st>>>(n, comm, newid);
   SB2_LAUNCH_CHECK(ctx);
   SB2_CUDA(cudaStreamSynchronize(st));
-  *n_comms = (int32_t)ids.size();
+  *n_comms = nc;
   return SB2_OK;
 }
 
@@ -654,7 +726,11 @@ extern "C" int32_t sb2_leiden_csr_f32(sb2_ctx* ctx, int64_t n, const int64_t* d_
           agg_insert_kernel<<<gridw(L.n), 256, 0, st>>>(L, rnew, slice, w.hkeys, w.hvals);
           SB2_LAUNCH_CHECK(ctx);
         }
-        agg_count_kernel<<<gridw(nc), 256, 0, st>>>(nc, slice, w.hkeys, cnt);
+        // mapping by mean slice length: warp per super-vertex while slices are short, CTA per super-vertex at
+        // the coarse levels where a few thousand super-vertices own millions of slots
+        const bool coarse = eL > (int64_t)nc * 256;
+        if (coarse) agg_count_block_kernel<<<(unsigned)nc, 256, 0, st>>>(nc, slice, w.hkeys, cnt);
+        else agg_count_kernel<<<gridw(nc), 256, 0, st>>>(nc, slice, w.hkeys, cnt);
         SB2_LAUNCH_CHECK(ctx);
         int64_t* indptr_new;
         SB2_TRY(lvl.alloc(&indptr_new, (size_t)nc + 1));
@@ -667,7 +743,8 @@ extern "C" int32_t sb2_leiden_csr_f32(sb2_ctx* ctx, int64_t n, const int64_t* d_
         SB2_TRY(lvl.alloc(&indices_new, (size_t)std::max<int64_t>(nnz_new, 1)));
         SB2_TRY(lvl.alloc(&w_new, (size_t)std::max<int64_t>(nnz_new, 1)));
         SB2_TRY(lvl.alloc(&k_new, (size_t)nc));
-        agg_fill_kernel<<<gridw(nc), 256, 0, st>>>(nc, slice, w.hkeys, w.hvals, indptr_new, indices_new, w_new);
+        if (coarse) agg_fill_block_kernel<<<(unsigned)nc, 256, 0, st>>>(nc, slice, w.hkeys, w.hvals, indptr_new, indices_new, w_new);
+        else agg_fill_kernel<<<gridw(nc), 256, 0, st>>>(nc, slice, w.hkeys, w.hvals, indptr_new, indices_new, w_new);
         SB2_LAUNCH_CHECK(ctx);
         SB2_CUDA(cudaMemsetAsync(w.counter + 2, 0, sizeof(u64), st));
         strength_kernel<<<gridt(nc), 256, 0, st>>>(nc, indptr_new, w_new, k_new, w.counter + 2);
@@ -692,7 +769,7 @@ extern "C" int32_t sb2_leiden_csr_f32(sb2_ctx* ctx, int64_t n, const int64_t* d_
   }
   pt.reset();
   SB2_TRY(renumber_device(ctx, scr, n, d_membership, h_n_comms));
-  SB2_TRY(quality_device(ctx, scr, n0, d_indptr, d_indices, wfx0, kfx0, total, resolution, d_membership, h_modularity));
+  SB2_TRY(quality_device(ctx, scr, n0, d_indptr, d_indices, wfx0, kfx0, total, resolution, d_membership, h_modularity, *h_n_comms));
   pt.lap(&t_fin);
   if (pt.on)
     fprintf(stderr, "[sb2 leiden] n=%d passes=%d local_move %.1f ms (%d calls) refine %.1f ms aggregate %.1f ms finalize %.1f ms\n",
