@@ -132,8 +132,9 @@ int32_t sb2_csr_gram(sb2_ctx* ctx, int64_t n, int32_t g, const int64_t* d_indptr
  * array (q0 % 128 == 0 unless n_query == n_points).  k includes the query itself: column 0 of
  * the outputs is the query row with distance 0 (src/scanpy/neighbors/_common.py:74-98).
  * Outputs [n_query x k]: d_idx int32 (global row ids), d_dist float64, ascending by (distance, id).
- * Exactness: a fast fp32 pass proposes 32 candidates per query, an fp64 re-score certifies the
- * top-k against a rounding-error bound, uncertified rows are recomputed exactly. */
+ * k <= 56 (k <= 30 when d > 52).  Exactness: a fast first pass (tcgen05 split-fp16 for d <= 52, fp32 FFMA otherwise)
+ * proposes 32 (k <= 24) or 64 candidates per query, an fp64 re-score certifies the top-k against a rounding-error
+ * bound, uncertified rows are recomputed exactly. */
 int32_t sb2_knn_l2_f32(sb2_ctx* ctx, int64_t n_points, int32_t d, const float* d_x, int64_t q0, int64_t n_query,
                        int32_t k, int32_t* d_idx, double* d_dist, sb2_knn_info* info);
 

@@ -227,68 +227,96 @@ __device__ __forceinline__ bool lex_less(double ka, int ia, double kb, int ib) {
   return ka < kb || (ka == kb && ia < ib);
 }
 
+// R = proposals per lane: the list has 32*R entries (R = 1: 32 proposals, k <= 24 keeps a slack of >= 8;
+// R = 2: 64 proposals for k up to 56)
+template <int R>
 __global__ void knn_rescore_kernel(const float* __restrict__ X, int64_t n_points, int d, int64_t q0, int64_t n_query,
                                    int k, const float* __restrict__ cand_score, const int32_t* __restrict__ cand_idx,
                                    const unsigned int* __restrict__ maxnorm_bits, const float* __restrict__ inv_s2,
                                    double eps_coef, int32_t* __restrict__ idx_out,
                                    double* __restrict__ dist_out, int32_t* __restrict__ work_q,
                                    double* __restrict__ work_ub, unsigned long long* __restrict__ work_cnt) {
+  constexpr int LM = 32 * R;
   const int lane = threadIdx.x & 31;
   const int64_t ql = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (ql >= n_query) return;
   const int64_t q = q0 + ql;
   const float* xq = X + q * d;
-  const int32_t ci = cand_idx[ql * LISTM + lane];
-  const float cs = cand_score[ql * LISTM + lane];
-  double key = DBL_MAX;
+  double key[R];
+  int32_t id[R];
   double qn = 0.0;
-  {
+  float smin = INFINITY;
+  bool all_used = true;
+#pragma unroll
+  for (int r = 0; r < R; ++r) {
+    const int32_t ci = cand_idx[ql * LM + r * 32 + lane];
+    const float cs = cand_score[ql * LM + r * 32 + lane];
     const float* xc = X + (int64_t)(ci < 0 ? 0 : ci) * d;
-    double acc = 0.0;
+    double acc = 0.0, qq = 0.0;
     for (int j = 0; j < d; ++j) {
       const double a = xq[j];
       const double df = a - (double)xc[j];
       acc = fma(df, df, acc);
-      qn = fma(a, a, qn);
+      qq = fma(a, a, qq);
     }
-    if (ci >= 0) key = (ci == q) ? -1.0 : acc;
+    qn = qq;
+    key[r] = ci < 0 ? DBL_MAX : ((ci == q) ? -1.0 : acc);
+    id[r] = ci < 0 ? INT32_MAX : ci;
+    if (ci >= 0) smin = fminf(smin, cs); else all_used = false;
   }
-  int32_t id = ci < 0 ? INT32_MAX : ci;
-  // warp bitonic sort ascending by (key, id)
+  // bitonic sort of the 32*R elements (element e = r*32 + lane) ascending by (key, id)
 #pragma unroll
-  for (int kk = 2; kk <= 32; kk <<= 1) {
+  for (int kk = 2; kk <= LM; kk <<= 1) {
 #pragma unroll
     for (int j = kk >> 1; j > 0; j >>= 1) {
-      const double ok = __shfl_xor_sync(0xffffffffu, key, j);
-      const int32_t oi = __shfl_xor_sync(0xffffffffu, id, j);
-      const bool want_min = ((lane & j) == 0) == ((lane & kk) == 0);
-      const bool other_less = lex_less(ok, oi, key, id);
-      const bool take = want_min ? other_less : lex_less(key, id, ok, oi);
-      if (take) { key = ok; id = oi; }
+      if (j >= 32) {  // partner lives in the same lane, other register (only R == 2, j == 32)
+        if (R == 2) {
+          const bool asc = true;  // kk == 64: final merge, ascending everywhere
+          const bool swap = lex_less(key[R - 1], id[R - 1], key[0], id[0]) == asc;
+          if (swap) {
+            const double tk = key[0]; key[0] = key[R - 1]; key[R - 1] = tk;
+            const int32_t ti = id[0]; id[0] = id[R - 1]; id[R - 1] = ti;
+          }
+        }
+      } else {
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+          const int e = r * 32 + lane;
+          const double ok = __shfl_xor_sync(0xffffffffu, key[r], j);
+          const int32_t oi = __shfl_xor_sync(0xffffffffu, id[r], j);
+          const bool want_min = ((e & j) == 0) == ((e & kk) == 0);
+          const bool other_less = lex_less(ok, oi, key[r], id[r]);
+          const bool take = want_min ? other_less : lex_less(key[r], id[r], ok, oi);
+          if (take) { key[r] = ok; id[r] = oi; }
+        }
+      }
     }
   }
-  // the query itself must sit in column 0 (src/scanpy/neighbors/_common.py:74-98); if it was not
-  // proposed at all (> 32 exact duplicates with smaller scores cannot happen: its own score is the
-  // row maximum up to rounding, but a flood of duplicates can push it out) the row is not certified.
-  const bool self_first = __shfl_sync(0xffffffffu, id, 0) == (int32_t)q;
-  const double kth = __shfl_sync(0xffffffffu, key, k - 1);
-  // worst proposal score (lists may be unsorted) and whether all 32 slots are in use
-  float s32 = ci >= 0 ? cs : INFINITY;
+  // the query itself must sit in column 0 (src/scanpy/neighbors/_common.py:74-98); if it was not proposed at
+  // all (a flood of exact duplicates can push it out of the list) the row is not certified.
+  const bool self_first = __shfl_sync(0xffffffffu, id[0], 0) == (int32_t)q;
+  const double kth = (R == 1 || k <= 32) ? __shfl_sync(0xffffffffu, key[0], (k - 1) & 31)
+                                          : __shfl_sync(0xffffffffu, key[R - 1], (k - 1) & 31);
+  // worst proposal score (lists are unsorted) and whether all slots are in use
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) s32 = fminf(s32, __shfl_xor_sync(0xffffffffu, s32, o));
-  const bool list_full = __all_sync(0xffffffffu, ci >= 0);
+  for (int o = 16; o > 0; o >>= 1) smin = fminf(smin, __shfl_xor_sync(0xffffffffu, smin, o));
+  const bool list_full = __all_sync(0xffffffffu, all_used);
   bool certified;
   if (!list_full) {
-    certified = true;  // fewer than 32 points exist: the proposal list is the whole data set
+    certified = true;  // fewer than 32*R points exist: the proposal list is the whole data set
   } else {
-    const double R = sqrt((double)__uint_as_float(*maxnorm_bits));
-    const double eps = eps_coef * (0.5 * R * R + sqrt(qn) * R);
-    const double bound = qn - 2.0 * ((double)s32 * (inv_s2 ? (double)*inv_s2 : 1.0) + eps);
+    const double Rn = sqrt((double)__uint_as_float(*maxnorm_bits));
+    const double eps = eps_coef * (0.5 * Rn * Rn + sqrt(qn) * Rn);
+    const double bound = qn - 2.0 * ((double)smin * (inv_s2 ? (double)*inv_s2 : 1.0) + eps);
     certified = self_first && (kth < bound);
   }
-  if (lane < k) {
-    idx_out[ql * k + lane] = id;
-    dist_out[ql * k + lane] = key < 0.0 ? 0.0 : sqrt(key);
+#pragma unroll
+  for (int r = 0; r < R; ++r) {
+    const int e = r * 32 + lane;
+    if (e < k) {
+      idx_out[ql * k + e] = id[r];
+      dist_out[ql * k + e] = key[r] < 0.0 ? 0.0 : sqrt(key[r]);
+    }
   }
   if (!certified && lane == 0) {
     const unsigned long long w = atomicAdd(work_cnt, 1ull);
@@ -392,7 +420,7 @@ extern "C" int32_t sb2_knn_l2_f32(sb2_ctx* ctx, int64_t n_points, int32_t d, con
   SB2_CHECK_ARG(n_points >= 1 && n_points < (int64_t)INT32_MAX - TILE, "n_points");
   // a query tile + two candidate stages of (d+1)*512 B must fit the 227 KB of shared memory
   SB2_CHECK_ARG(d >= 1 && d <= 150, "d must be in [1,150]");
-  SB2_CHECK_ARG(k >= 1 && k <= LISTM - 2 && k <= n_points, "k must be in [1,30] and <= n_points");
+  SB2_CHECK_ARG(k >= 1 && k <= 56 && k <= n_points, "k must be in [1,56] and <= n_points");
   SB2_CHECK_ARG(q0 >= 0 && n_query >= 0 && q0 + n_query <= n_points, "query range");
   SB2_CHECK_ARG(q0 % TILE == 0, "q0 must be a multiple of 128");
   if (n_query == 0) return SB2_OK;
@@ -410,8 +438,14 @@ extern "C" int32_t sb2_knn_l2_f32(sb2_ctx* ctx, int64_t n_points, int32_t d, con
   unsigned long long* work_cnt;
   SB2_TRY(scr.alloc(&Xt, (size_t)(n_tiles * chunk_f)));
   SB2_TRY(scr.alloc(&maxnorm, 4));
-  SB2_TRY(scr.alloc(&cand_score, (size_t)n_query * LISTM));
-  SB2_TRY(scr.alloc(&cand_idx, (size_t)n_query * LISTM));
+  // 32 proposals per query keep a slack of >= 8 behind k <= 24; larger k gets 64 (tensor path only: the FFMA pass
+  // keeps one proposal per lane, its rows then lean on the exact fallback)
+  const char* force = getenv("SB2_KNN_PASS1");
+  const bool use_tc = knn_tc_supported(d) && !(force && strcmp(force, "ffma") == 0);
+  const int list_m = (use_tc && k > 24) ? 64 : 32;
+  SB2_CHECK_ARG(k <= list_m - 2, "k > 30 needs the tensor-core pass (n_pcs <= 52)");
+  SB2_TRY(scr.alloc(&cand_score, (size_t)n_query * list_m));
+  SB2_TRY(scr.alloc(&cand_idx, (size_t)n_query * list_m));
   SB2_TRY(scr.alloc(&work_q, (size_t)n_query));
   SB2_TRY(scr.alloc(&work_ub, (size_t)n_query));
   SB2_TRY(scr.alloc(&work_cnt, 2));
@@ -431,14 +465,12 @@ extern "C" int32_t sb2_knn_l2_f32(sb2_ctx* ctx, int64_t n_points, int32_t d, con
   }
   double issued_flops = 2.0 * (double)n_query * (double)n_points * (double)d;
   // pass 1: tensor-core split-precision sweep (knn_tc.cu) when the concatenated K axis fits, else fp32 FFMA
-  const char* force = getenv("SB2_KNN_PASS1");
-  const bool use_tc = knn_tc_supported(d) && !(force && strcmp(force, "ffma") == 0);
   float* inv_s2 = nullptr;
   double eps_coef = 1.5 * (double)(d + 2) * 5.9604644775390625e-08;
   if (use_tc) {
     SB2_TRY(scr.alloc(&inv_s2, 4));
-    SB2_TRY(knn_tc_pass1(ctx, scr, d_x, n_points, d, maxnorm, q0, n_query, cand_score, cand_idx, inv_s2, &eps_coef, ev0,
-                         &issued_flops));
+    SB2_TRY(knn_tc_pass1(ctx, scr, d_x, n_points, d, maxnorm, q0, n_query, list_m, cand_score, cand_idx, inv_s2, &eps_coef,
+                         ev0, &issued_flops));
   } else {
     if (ev0) SB2_CUDA(cudaEventRecord(ev0, st));
     const int64_t q_tiles = ceil_div64(n_query, TILE);
@@ -460,9 +492,14 @@ extern "C" int32_t sb2_knn_l2_f32(sb2_ctx* ctx, int64_t n_points, int32_t d, con
   if (info) SB2_CUDA(cudaEventRecord(ev1, st));
   {
     const int wpb = 8;
-    knn_rescore_kernel<<<(unsigned)ceil_div64(n_query, wpb), wpb * 32, 0, st>>>(
-        d_x, n_points, d, q0, n_query, k, cand_score, cand_idx, maxnorm, inv_s2, eps_coef, d_idx, d_dist, work_q, work_ub,
-        work_cnt);
+    if (list_m == 32)
+      knn_rescore_kernel<1><<<(unsigned)ceil_div64(n_query, wpb), wpb * 32, 0, st>>>(
+          d_x, n_points, d, q0, n_query, k, cand_score, cand_idx, maxnorm, inv_s2, eps_coef, d_idx, d_dist, work_q, work_ub,
+          work_cnt);
+    else
+      knn_rescore_kernel<2><<<(unsigned)ceil_div64(n_query, wpb), wpb * 32, 0, st>>>(
+          d_x, n_points, d, q0, n_query, k, cand_score, cand_idx, maxnorm, inv_s2, eps_coef, d_idx, d_dist, work_q, work_ub,
+          work_cnt);
     SB2_LAUNCH_CHECK(ctx);
   }
   {

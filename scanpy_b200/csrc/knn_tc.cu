@@ -184,9 +184,10 @@ knn_tc_prep_kernel(const float* __restrict__ X, int64_t n, int d, int kpad, cons
 // Per-row proposal list: 32 scores in REGISTERS (4 groups of 8 with a running minimum per group), ids in
 // global memory (write-only).  tau = min of the list = the score a candidate must beat.  All indexing is
 // static (macro-expanded), so nothing spills and an insertion never waits on memory.
+template <int NG>  // NG groups of 8 proposals: 32 (NG = 4) or 64 (NG = 8)
 struct RowList {
-  float ls[32];
-  float gm[4];
+  float ls[8 * NG];
+  float gm[NG];
   float tau;
 };
 __device__ __forceinline__ float min8(const float* x) {
@@ -203,14 +204,22 @@ __device__ __forceinline__ float min8(const float* x) {
     }                                                                         \
     L.gm[(G)] = min8(&L.ls[(G) * 8]);                                         \
   }
-__device__ __forceinline__ void list_insert(RowList& L, int32_t* __restrict__ id, float v, int32_t cand) {
+template <int NG>
+__device__ __forceinline__ void list_insert(RowList<NG>& L, int32_t* __restrict__ id, float v, int32_t cand) {
   int pos = 0;
   if (L.gm[0] == L.tau) SB2_GROUP_INSERT(0)
   else if (L.gm[1] == L.tau) SB2_GROUP_INSERT(1)
   else if (L.gm[2] == L.tau) SB2_GROUP_INSERT(2)
-  else SB2_GROUP_INSERT(3)
+  else if (NG == 4 || L.gm[3] == L.tau) SB2_GROUP_INSERT(3)
+  else if (L.gm[4 % NG] == L.tau) SB2_GROUP_INSERT(4 % NG)
+  else if (L.gm[5 % NG] == L.tau) SB2_GROUP_INSERT(5 % NG)
+  else if (L.gm[6 % NG] == L.tau) SB2_GROUP_INSERT(6 % NG)
+  else SB2_GROUP_INSERT(7 % NG)
   id[pos] = cand;
-  L.tau = fminf(fminf(L.gm[0], L.gm[1]), fminf(L.gm[2], L.gm[3]));
+  float t = L.gm[0];
+#pragma unroll
+  for (int g = 1; g < NG; ++g) t = fminf(t, L.gm[g]);
+  L.tau = t;
 }
 // examine one 32-column chunk of the row (values already in registers).  Fast path: a 3-input max tree and
 // one compare.  Rare path (about 340 times per row over a 1.3M sweep): pull out the chunk's maxima one by one
@@ -222,7 +231,8 @@ __device__ __forceinline__ float max32(const uint32_t (&v)[32]) {
   for (int j = 1; j < 32; ++j) m = fmaxf(m, __uint_as_float(v[j]));
   return m;
 }
-__device__ __forceinline__ void scan_chunk(RowList& L, int32_t* __restrict__ id, uint32_t (&v)[32], int32_t cand0,
+template <int NG>
+__device__ __forceinline__ void scan_chunk(RowList<NG>& L, int32_t* __restrict__ id, uint32_t (&v)[32], int32_t cand0,
                                            int32_t n_points) {
   float m = max32(v);
   while (m > L.tau) {
@@ -251,6 +261,7 @@ __device__ __forceinline__ void tmem_ld32_nowait(uint32_t taddr, uint32_t (&v)[3
       : "r"(taddr));
 }
 
+template <int NG>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 knn_pass1_tc_kernel(const __half* __restrict__ Aimg, const __half* __restrict__ Bimg, int kpad, int64_t n_btiles,
                     int64_t qtile0, int64_t n_query, int32_t n_points, float* __restrict__ cand_score,
@@ -331,17 +342,18 @@ knn_pass1_tc_kernel(const __half* __restrict__ Aimg, const __half* __restrict__ 
     const int row = lgrp * 32 + lane;
     const int64_t ql = ((int64_t)blockIdx.x * 2 + h) * TM + row;  // local query index
     const bool valid = ql < n_query;
-    float* sc = cand_score + (valid ? ql : 0) * LISTM;
-    int32_t* id = cand_idx + (valid ? ql : 0) * LISTM;
-    RowList L;
+    constexpr int LM = 8 * NG;
+    float* sc = cand_score + (valid ? ql : 0) * LM;
+    int32_t* id = cand_idx + (valid ? ql : 0) * LM;
+    RowList<NG> L;
 #pragma unroll
-    for (int i = 0; i < 32; ++i) L.ls[i] = -INFINITY;
+    for (int i = 0; i < LM; ++i) L.ls[i] = -INFINITY;
 #pragma unroll
-    for (int g = 0; g < 4; ++g) L.gm[g] = -INFINITY;
+    for (int g = 0; g < NG; ++g) L.gm[g] = -INFINITY;
     L.tau = valid ? -INFINITY : INFINITY;  // rows past n_query never accept anything
     if (valid) {
 #pragma unroll
-      for (int i = 0; i < LISTM; ++i) id[i] = -1;
+      for (int i = 0; i < LM; ++i) id[i] = -1;
     }
     for (int64_t c = 0; c < n_btiles; ++c) {
       const int b = (int)(c & 1);
@@ -367,7 +379,7 @@ knn_pass1_tc_kernel(const __half* __restrict__ Aimg, const __half* __restrict__ 
     }
     if (valid) {
 #pragma unroll
-      for (int i = 0; i < LISTM; ++i) sc[i] = L.ls[i];
+      for (int i = 0; i < LM; ++i) sc[i] = L.ls[i];
     }
   }
   tc_fence_before();
@@ -382,7 +394,7 @@ knn_pass1_tc_kernel(const __half* __restrict__ Aimg, const __half* __restrict__ 
 bool knn_tc_supported(int d) { return 3 * d + 3 <= 160; }
 
 int32_t knn_tc_pass1(sb2_ctx* ctx, ScratchScope& scr, const float* d_x, int64_t n_points, int d,
-                     const unsigned int* d_maxnorm_bits, int64_t q0, int64_t n_query, float* cand_score,
+                     const unsigned int* d_maxnorm_bits, int64_t q0, int64_t n_query, int list_m, float* cand_score,
                      int32_t* cand_idx, float* d_inv_s2, double* eps_coef, cudaEvent_t ev_after_prep,
                      double* issued_flops) {
   cudaStream_t st = ctx->stream;
@@ -400,10 +412,17 @@ int32_t knn_tc_pass1(sb2_ctx* ctx, ScratchScope& scr, const float* d_x, int64_t 
   const uint32_t tile_b = (uint32_t)TM * kpad * 2;
   const size_t smem = (size_t)(2 + NSTAGE) * tile_b + 128;
   SB2_CHECK_ARG(smem <= ctx->prop.sharedMemPerBlockOptin, "tensor-core kNN tile does not fit shared memory");
-  SB2_CUDA(cudaFuncSetAttribute(knn_pass1_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int64_t q_ctas = ceil_div64(n_query, 2 * TM);
-  knn_pass1_tc_kernel<<<(unsigned)q_ctas, TC_THREADS, smem, st>>>(Aimg, Bimg, kpad, n_tiles, q0 / TM, n_query,
-                                                                  (int32_t)n_points, cand_score, cand_idx);
+  if (list_m == 32) {
+    SB2_CUDA(cudaFuncSetAttribute(knn_pass1_tc_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    knn_pass1_tc_kernel<4><<<(unsigned)q_ctas, TC_THREADS, smem, st>>>(Aimg, Bimg, kpad, n_tiles, q0 / TM, n_query,
+                                                                       (int32_t)n_points, cand_score, cand_idx);
+  } else {
+    SB2_CHECK_ARG(list_m == 64, "list_m must be 32 or 64");
+    SB2_CUDA(cudaFuncSetAttribute(knn_pass1_tc_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    knn_pass1_tc_kernel<8><<<(unsigned)q_ctas, TC_THREADS, smem, st>>>(Aimg, Bimg, kpad, n_tiles, q0 / TM, n_query,
+                                                                       (int32_t)n_points, cand_score, cand_idx);
+  }
   SB2_LAUNCH_CHECK(ctx);
   // error of the split-precision score, relative to (R^2/2 + |q| R): operand split 3*2^-24 + dropped lo*lo 2^-24
   // + fp16 three-way norm 2^-33 + fp32 accumulation over kpad products in the tensor pipe (bounded generously)

@@ -143,7 +143,7 @@ def test_knn_golden_pbmc68k(pbmc68k_graph):
 
 
 @pytest.mark.parametrize("n,d,k", [(1, 3, 1), (5, 2, 5), (127, 7, 15), (129, 50, 15), (1000, 50, 30), (4097, 33, 10),
-                                   (12345, 50, 15), (3000, 100, 30), (2000, 150, 8)])
+                                   (12345, 50, 15), (3000, 100, 30), (2000, 150, 8), (6000, 50, 30), (5000, 40, 45), (100, 8, 56)])
 def test_knn_identical_index_sets(n, d, k):
     rs = np.random.RandomState(n + d)
     x = rs.standard_normal((n, d)).astype(np.float32)
@@ -180,7 +180,9 @@ def test_knn_rejects_unsupported_shapes():
     with pytest.raises(sb._abi.B200Error, match="d must be in"):
         _ops.knn(x, 5)
     with pytest.raises(sb._abi.B200Error, match="k must be in"):
-        _ops.knn(x[:, :10], 31)
+        _ops.knn(x[:, :10], 57)
+    with pytest.raises(sb._abi.B200Error, match="k > 30 needs the tensor-core pass"):
+        _ops.knn(x[:, :100], 31)
 
 
 def test_knn_transformer_in_reference_pipeline_shape():
