@@ -443,7 +443,7 @@ extern "C" int32_t sb2_knn_l2_f32(sb2_ctx* ctx, int64_t n_points, int32_t d, con
   const char* force = getenv("SB2_KNN_PASS1");
   const bool use_tc = knn_tc_supported(d) && !(force && strcmp(force, "ffma") == 0);
   const int list_m = (use_tc && k > 24) ? 64 : 32;
-  SB2_CHECK_ARG(k <= list_m - 2, "k > 30 needs the tensor-core pass (n_pcs <= 52)");
+  SB2_CHECK_ARG(k <= list_m - 2, "k > 30 needs the tensor-core pass (SB2_KNN_PASS1=ffma limits k to 30)");
   SB2_TRY(scr.alloc(&cand_score, (size_t)n_query * list_m));
   SB2_TRY(scr.alloc(&cand_idx, (size_t)n_query * list_m));
   SB2_TRY(scr.alloc(&work_q, (size_t)n_query));

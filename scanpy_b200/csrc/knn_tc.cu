@@ -261,16 +261,19 @@ __device__ __forceinline__ void tmem_ld32_nowait(uint32_t taddr, uint32_t (&v)[3
       : "r"(taddr));
 }
 
-template <int NG>
+// QH = query halves per CTA (2: 256 queries, 1: 128 queries); nsplit = pieces the K axis of a candidate image is
+// staged in (1 when a whole image fits a ring stage; 2 or 4 for wide embeddings, d up to 150).
+template <int NG, int QH>
 __global__ void __launch_bounds__(TC_THREADS, 1)
-knn_pass1_tc_kernel(const __half* __restrict__ Aimg, const __half* __restrict__ Bimg, int kpad, int64_t n_btiles,
+knn_pass1_tc_kernel(const __half* __restrict__ Aimg, const __half* __restrict__ Bimg, int kpad, int nsplit, int64_t n_btiles,
                     int64_t qtile0, int64_t n_query, int32_t n_points, float* __restrict__ cand_score,
                     int32_t* __restrict__ cand_idx) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   const uint32_t tile_b = (uint32_t)TM * (uint32_t)kpad * 2u;  // bytes per 128-row image
-  unsigned char* As = smem_raw;                     // 2 images (256 queries)
-  unsigned char* Bs0 = smem_raw + 2 * tile_b;       // NSTAGE images
-  uint64_t* bars = reinterpret_cast<uint64_t*>(Bs0 + (size_t)NSTAGE * tile_b);
+  const uint32_t part_b = tile_b / (uint32_t)nsplit;  // bytes per staged K-slice of a candidate image
+  unsigned char* As = smem_raw;                     // QH images (128*QH queries)
+  unsigned char* Bs0 = smem_raw + QH * tile_b;      // NSTAGE slices
+  uint64_t* bars = reinterpret_cast<uint64_t*>(Bs0 + (size_t)NSTAGE * part_b);
   uint64_t* full = bars;                  // [NSTAGE] producer -> MMA
   uint64_t* empty = bars + NSTAGE;        // [NSTAGE] MMA (commit) -> producer
   uint64_t* afull = bars + 2 * NSTAGE;    // [1]
@@ -282,7 +285,7 @@ knn_pass1_tc_kernel(const __half* __restrict__ Aimg, const __half* __restrict__ 
   if (threadIdx.x == 0) {
     for (int s = 0; s < NSTAGE; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
     mbar_init(afull, 1);
-    for (int b = 0; b < 2; ++b) { mbar_init(&tfull[b], 1); mbar_init(&tempty[b], 8); }
+    for (int b = 0; b < 2; ++b) { mbar_init(&tfull[b], 1); mbar_init(&tempty[b], 4 * QH); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -293,19 +296,22 @@ knn_pass1_tc_kernel(const __half* __restrict__ Aimg, const __half* __restrict__ 
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  const int nks = kpad / 16;  // k-steps per tile
+  const int nks = kpad / 16 / nsplit;  // k-steps per staged slice
 
   if (warp == 0) {
     // ---------------- producer ----------------
     if (lane == 0) {
-      mbar_expect_tx(afull, 2 * tile_b);
-      bulk_g2s(As, reinterpret_cast<const unsigned char*>(Aimg) + (size_t)(qtile0 + 2 * (int64_t)blockIdx.x) * tile_b, 2 * tile_b, afull);
-      for (int64_t c = 0; c < n_btiles; ++c) {
-        const int s = (int)(c % NSTAGE);
-        const int64_t use = c / NSTAGE;
+      mbar_expect_tx(afull, QH * tile_b);
+      for (int h = 0; h < QH; ++h)
+        bulk_g2s(As + (size_t)h * tile_b,
+                 reinterpret_cast<const unsigned char*>(Aimg) + (size_t)(qtile0 + QH * (int64_t)blockIdx.x + h) * tile_b, tile_b, afull);
+      const int64_t n_it = n_btiles * nsplit;  // slices are contiguous in the image stream
+      for (int64_t it = 0; it < n_it; ++it) {
+        const int s = (int)(it % NSTAGE);
+        const int64_t use = it / NSTAGE;
         if (use > 0) mbar_wait(&empty[s], (uint32_t)((use - 1) & 1));
-        mbar_expect_tx(&full[s], tile_b);
-        bulk_g2s(Bs0 + (size_t)s * tile_b, reinterpret_cast<const unsigned char*>(Bimg) + (size_t)c * tile_b, tile_b, &full[s]);
+        mbar_expect_tx(&full[s], part_b);
+        bulk_g2s(Bs0 + (size_t)s * part_b, reinterpret_cast<const unsigned char*>(Bimg) + (size_t)it * part_b, part_b, &full[s]);
       }
     }
   } else if (warp == 1) {
@@ -313,34 +319,37 @@ knn_pass1_tc_kernel(const __half* __restrict__ Aimg, const __half* __restrict__ 
     if (lane == 0) {
       mbar_wait(afull, 0);
       const uint32_t a_addr = smem_u32(As);
+      int64_t it = 0;
       for (int64_t c = 0; c < n_btiles; ++c) {
-        const int s = (int)(c % NSTAGE);
         const int b = (int)(c & 1);
         const int64_t useb = c >> 1;
-        mbar_wait(&full[s], (uint32_t)((c / NSTAGE) & 1));
-        if (useb > 0) mbar_wait(&tempty[b], (uint32_t)((useb - 1) & 1));
-        tc_fence_after();
-        const uint32_t b_addr = smem_u32(Bs0 + (size_t)s * tile_b);
+        for (int p = 0; p < nsplit; ++p, ++it) {
+          const int s = (int)(it % NSTAGE);
+          mbar_wait(&full[s], (uint32_t)((it / NSTAGE) & 1));
+          if (p == 0 && useb > 0) mbar_wait(&tempty[b], (uint32_t)((useb - 1) & 1));
+          tc_fence_after();
+          const uint32_t b_addr = smem_u32(Bs0 + (size_t)s * part_b);
 #pragma unroll
-        for (int h = 0; h < 2; ++h) {
-          const uint32_t tm = tmem_base + (uint32_t)(b * 256 + h * 128);
-          for (int j = 0; j < nks; ++j) {
-            const uint64_t da = umma_desc(a_addr + (uint32_t)h * tile_b + (uint32_t)j * 2u * LBO);
-            const uint64_t db = umma_desc(b_addr + (uint32_t)j * 2u * LBO);
-            umma_f16(tm, da, db, j > 0 ? 1u : 0u);
+          for (int h = 0; h < QH; ++h) {
+            const uint32_t tm = tmem_base + (uint32_t)(b * (128 * QH) + h * 128);
+            for (int j = 0; j < nks; ++j) {
+              const uint64_t da = umma_desc(a_addr + (uint32_t)h * tile_b + (uint32_t)(p * nks + j) * 2u * LBO);
+              const uint64_t db = umma_desc(b_addr + (uint32_t)j * 2u * LBO);
+              umma_f16(tm, da, db, (p > 0 || j > 0) ? 1u : 0u);
+            }
           }
+          tc_commit(&empty[s]);   // smem stage reusable once these MMAs have read it
         }
-        tc_commit(&empty[s]);   // smem stage reusable once these MMAs have read it
-        tc_commit(&tfull[b]);   // accumulators of buffer b complete
+        tc_commit(&tfull[b]);     // accumulators of buffer b complete
       }
     }
-  } else {
+  } else if (((warp - 2) >> 2) < QH) {
     // ---------------- epilogue: thread <-> query row ----------------
     const int e = warp - 2;                 // 0..7
     const int h = e >> 2;                   // query half
     const int lgrp = warp & 3;              // TMEM lane group this warp may access
     const int row = lgrp * 32 + lane;
-    const int64_t ql = ((int64_t)blockIdx.x * 2 + h) * TM + row;  // local query index
+    const int64_t ql = ((int64_t)blockIdx.x * QH + h) * TM + row;  // local query index
     const bool valid = ql < n_query;
     constexpr int LM = 8 * NG;
     float* sc = cand_score + (valid ? ql : 0) * LM;
@@ -359,7 +368,7 @@ knn_pass1_tc_kernel(const __half* __restrict__ Aimg, const __half* __restrict__ 
       const int b = (int)(c & 1);
       mbar_wait(&tfull[b], (uint32_t)((c >> 1) & 1));
       tc_fence_after();
-      const uint32_t tbase = tmem_base + ((uint32_t)(lgrp * 32) << 16) + (uint32_t)(b * 256 + h * 128);
+      const uint32_t tbase = tmem_base + ((uint32_t)(lgrp * 32) << 16) + (uint32_t)(b * (128 * QH) + h * 128);
       const int32_t cbase = (int32_t)(c * TM);
 #pragma unroll 1
       for (int half = 0; half < 2; ++half) {
@@ -391,16 +400,39 @@ knn_pass1_tc_kernel(const __half* __restrict__ Aimg, const __half* __restrict__ 
 
 }  // namespace
 
-bool knn_tc_supported(int d) { return 3 * d + 3 <= 160; }
+// widest K axis the kernel can stage: one query image + NSTAGE quarter-slices of a candidate image in 227 KB
+bool knn_tc_supported(int d) { return 3 * d + 3 <= 512; }
+
+namespace {
+template <int NG, int QH>
+cudaError_t launch_tc(unsigned grid, size_t smem, cudaStream_t st, const __half* A, const __half* B, int kpad, int nsplit,
+                      int64_t n_tiles, int64_t qtile0, int64_t n_query, int32_t n_points, float* cs, int32_t* ci) {
+  cudaError_t e = cudaFuncSetAttribute(knn_pass1_tc_kernel<NG, QH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  knn_pass1_tc_kernel<NG, QH><<<grid, TC_THREADS, smem, st>>>(A, B, kpad, nsplit, n_tiles, qtile0, n_query, n_points, cs, ci);
+  return cudaSuccess;
+}
+}  // namespace
 
 int32_t knn_tc_pass1(sb2_ctx* ctx, ScratchScope& scr, const float* d_x, int64_t n_points, int d,
                      const unsigned int* d_maxnorm_bits, int64_t q0, int64_t n_query, int list_m, float* cand_score,
                      int32_t* cand_idx, float* d_inv_s2, double* eps_coef, cudaEvent_t ev_after_prep,
                      double* issued_flops) {
   cudaStream_t st = ctx->stream;
-  const int kpad = ((3 * d + 3 + 15) / 16) * 16;
+  // tile shape: 256 queries per CTA with whole candidate images per stage when that fits (d <= 52); otherwise
+  // 128 queries per CTA and the candidate K axis staged in 1, 2 or 4 slices
+  const size_t smem_cap = ctx->prop.sharedMemPerBlockOptin;
+  int qh = 0, nsplit = 0, kpad = 0;
+  const int cand[4][2] = {{2, 1}, {1, 1}, {1, 2}, {1, 4}};
+  for (int t = 0; t < 4 && !qh; ++t) {
+    const int unit = 16 * cand[t][1];
+    const int kp = ((3 * d + 3 + unit - 1) / unit) * unit;
+    const size_t tb = (size_t)TM * kp * 2;
+    if (cand[t][0] * tb + NSTAGE * (tb / cand[t][1]) + 128 <= smem_cap) { qh = cand[t][0]; nsplit = cand[t][1]; kpad = kp; }
+  }
+  SB2_CHECK_ARG(qh != 0, "tensor-core kNN tile does not fit shared memory");
   int64_t n_tiles = ceil_div64(n_points, TM);
-  const int64_t n_tiles_alloc = n_tiles + (n_tiles & 1) + 2;  // A images are consumed in pairs
+  const int64_t n_tiles_alloc = n_tiles + (n_tiles & 1) + 2;  // A images may be consumed in pairs
   const size_t img_halves = (size_t)TM * kpad;
   __half *Aimg, *Bimg;
   SB2_TRY(scr.alloc(&Aimg, (size_t)n_tiles_alloc * img_halves));
@@ -408,24 +440,24 @@ int32_t knn_tc_pass1(sb2_ctx* ctx, ScratchScope& scr, const float* d_x, int64_t 
   knn_tc_prep_kernel<<<(unsigned)n_tiles_alloc, 256, 0, st>>>(d_x, n_points, d, kpad, d_maxnorm_bits, Aimg, Bimg, d_inv_s2);
   SB2_LAUNCH_CHECK(ctx);
   if (ev_after_prep) SB2_CUDA(cudaEventRecord(ev_after_prep, st));
-  if (issued_flops) *issued_flops = 2.0 * (double)(ceil_div64(n_query, 2 * TM) * 2 * TM) * (double)(n_tiles * TM) * (double)kpad;
+  const int64_t q_ctas = ceil_div64(n_query, (int64_t)qh * TM);
+  if (issued_flops) *issued_flops = 2.0 * (double)(q_ctas * qh * TM) * (double)(n_tiles * TM) * (double)kpad;
   const uint32_t tile_b = (uint32_t)TM * kpad * 2;
-  const size_t smem = (size_t)(2 + NSTAGE) * tile_b + 128;
-  SB2_CHECK_ARG(smem <= ctx->prop.sharedMemPerBlockOptin, "tensor-core kNN tile does not fit shared memory");
-  const int64_t q_ctas = ceil_div64(n_query, 2 * TM);
-  if (list_m == 32) {
-    SB2_CUDA(cudaFuncSetAttribute(knn_pass1_tc_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    knn_pass1_tc_kernel<4><<<(unsigned)q_ctas, TC_THREADS, smem, st>>>(Aimg, Bimg, kpad, n_tiles, q0 / TM, n_query,
-                                                                       (int32_t)n_points, cand_score, cand_idx);
-  } else {
-    SB2_CHECK_ARG(list_m == 64, "list_m must be 32 or 64");
-    SB2_CUDA(cudaFuncSetAttribute(knn_pass1_tc_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    knn_pass1_tc_kernel<8><<<(unsigned)q_ctas, TC_THREADS, smem, st>>>(Aimg, Bimg, kpad, n_tiles, q0 / TM, n_query,
-                                                                       (int32_t)n_points, cand_score, cand_idx);
-  }
+  const size_t smem = (size_t)qh * tile_b + (size_t)NSTAGE * (tile_b / nsplit) + 128;
+  SB2_CHECK_ARG(list_m == 32 || list_m == 64, "list_m must be 32 or 64");
+  cudaError_t le;
+  const unsigned grid = (unsigned)q_ctas;
+  const int64_t qt0 = q0 / TM;
+  const int32_t np = (int32_t)n_points;
+  if (list_m == 32 && qh == 2) le = launch_tc<4, 2>(grid, smem, st, Aimg, Bimg, kpad, nsplit, n_tiles, qt0, n_query, np, cand_score, cand_idx);
+  else if (list_m == 32) le = launch_tc<4, 1>(grid, smem, st, Aimg, Bimg, kpad, nsplit, n_tiles, qt0, n_query, np, cand_score, cand_idx);
+  else if (qh == 2) le = launch_tc<8, 2>(grid, smem, st, Aimg, Bimg, kpad, nsplit, n_tiles, qt0, n_query, np, cand_score, cand_idx);
+  else le = launch_tc<8, 1>(grid, smem, st, Aimg, Bimg, kpad, nsplit, n_tiles, qt0, n_query, np, cand_score, cand_idx);
+  SB2_CUDA(le);
   SB2_LAUNCH_CHECK(ctx);
   // error of the split-precision score, relative to (R^2/2 + |q| R): operand split 3*2^-24 + dropped lo*lo 2^-24
-  // + fp16 three-way norm 2^-33 + fp32 accumulation over kpad products in the tensor pipe (bounded generously)
-  *eps_coef = 256.0 * 5.9604644775390625e-08;
+  // + fp16 three-way norm 2^-33 + fp32 accumulation in the tensor pipe: kpad/16 accumulator updates of one ulp
+  // each plus the alignment loss inside a 16-product group, bounded by 1.6 * kpad * 2^-24 of sum |a_i b_i|
+  *eps_coef = (1.6 * kpad + 8.0) * 5.9604644775390625e-08;
   return SB2_OK;
 }

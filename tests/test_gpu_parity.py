@@ -143,7 +143,11 @@ def test_knn_golden_pbmc68k(pbmc68k_graph):
 
 
 @pytest.mark.parametrize("n,d,k", [(1, 3, 1), (5, 2, 5), (127, 7, 15), (129, 50, 15), (1000, 50, 30), (4097, 33, 10),
-                                   (12345, 50, 15), (3000, 100, 30), (2000, 150, 8), (6000, 50, 30), (5000, 40, 45), (100, 8, 56)])
+                                   (12345, 50, 15), (3000, 100, 30), (2000, 150, 8), (6000, 50, 30), (5000, 40, 45), (100, 8, 56),
+                                   # tile-shape boundaries of the tensor-core pass (knn_tc.cu: 256-query CTAs up to d = 57,
+                                   # then 128-query CTAs with the K axis staged in 1 / 2 / 4 slices)
+                                   (3000, 57, 15), (3000, 58, 15), (2500, 73, 40), (2500, 74, 15), (2500, 116, 15),
+                                   (2500, 117, 30), (3000, 150, 56)])
 def test_knn_identical_index_sets(n, d, k):
     rs = np.random.RandomState(n + d)
     x = rs.standard_normal((n, d)).astype(np.float32)
@@ -181,8 +185,19 @@ def test_knn_rejects_unsupported_shapes():
         _ops.knn(x, 5)
     with pytest.raises(sb._abi.B200Error, match="k must be in"):
         _ops.knn(x[:, :10], 57)
+
+
+def test_knn_ffma_pass_still_exact(monkeypatch):
+    # the CUDA-core first pass stays selectable (SB2_KNN_PASS1=ffma, read per call by sb2_knn_l2_f32); same exact result
+    monkeypatch.setenv("SB2_KNN_PASS1", "ffma")
+    rs = np.random.RandomState(11)
+    x = rs.standard_normal((3000, 100)).astype(np.float32)
+    idx, dist, info = _ops.knn(x, 30)
+    assert info["pass1_tensor"] == 0
+    oi, od = oknn.knn_brute(x, 30)
+    assert oknn.same_neighbor_sets(idx, dist, oi, od).all()
     with pytest.raises(sb._abi.B200Error, match="k > 30 needs the tensor-core pass"):
-        _ops.knn(x[:, :100], 31)
+        _ops.knn(x, 31)
 
 
 def test_knn_transformer_in_reference_pipeline_shape():
