@@ -68,10 +68,11 @@ typedef struct sb2_pca_info {
 typedef struct sb2_knn_info {
   int64_t n_uncertified;    /* query rows that needed the exact fallback */
   float max_norm;
-  float pass1_ms;           /* CUDA-event duration of knn_pass1_kernel on the ctx stream */
+  float pass1_ms;           /* CUDA-event duration of all first-pass sweep launches on the ctx stream */
   double pass1_flops;       /* 2 * n_query * n_points * d: the algorithmic flops of that launch */
   double pass1_issued_flops; /* flops actually issued (tensor path: padded tiles x split-precision K axis) */
   int32_t pass1_tensor;     /* 1 = knn_pass1_tc_kernel (tcgen05), 0 = knn_pass1_kernel (fp32 FFMA) */
+  int64_t n_resweep;        /* rows the fp16 tier left uncertified, swept again in split precision (tensor path) */
 } sb2_knn_info;
 
 typedef struct sb2_leiden_info {

@@ -39,7 +39,7 @@ class PcaInfo(ctypes.Structure):
 
 class KnnInfo(ctypes.Structure):
     _fields_ = [("n_uncertified", c_int64), ("max_norm", c_float), ("pass1_ms", c_float), ("pass1_flops", c_double),
-                ("pass1_issued_flops", c_double), ("pass1_tensor", c_int32)]
+                ("pass1_issued_flops", c_double), ("pass1_tensor", c_int32), ("n_resweep", c_int64)]
 
 
 class LeidenInfo(ctypes.Structure):

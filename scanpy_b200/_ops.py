@@ -104,7 +104,7 @@ def knn_device(ctx, d_x, n_neighbors: int, *, q0: int = 0, n_query: int | None =
                                  byref(info)))
     return idx, dist, dict(n_uncertified=int(info.n_uncertified), max_norm=float(info.max_norm),
                            pass1_ms=float(info.pass1_ms), pass1_flops=float(info.pass1_flops),
-                           pass1_issued_flops=float(info.pass1_issued_flops), pass1_tensor=int(info.pass1_tensor))
+                           pass1_issued_flops=float(info.pass1_issued_flops), pass1_tensor=int(info.pass1_tensor), n_resweep=int(info.n_resweep))
 
 
 def knn(x: np.ndarray, n_neighbors: int, *, ctx=None):
@@ -171,7 +171,8 @@ def knn_connectivities(knn_indices: np.ndarray, knn_dists: np.ndarray, method: s
 
 def knn_and_connectivities(x: np.ndarray, n_neighbors: int, *, ctx=None):
     """Exact kNN + UMAP connectivities with the (idx, dist) lists kept on the device in between.
-    -> (indices int32 [n,k], distances float64 [n,k], connectivities scipy CSR float32)."""
+    -> (distances scipy CSR float64 [n,n] with k-1 entries per row: the self column is dropped ON THE DEVICE, so the
+    host never re-strides the n x k lists; connectivities scipy CSR float32)."""
     from scipy import sparse
 
     ctx = ctx or _abi.default_context()
@@ -179,9 +180,17 @@ def knn_and_connectivities(x: np.ndarray, n_neighbors: int, *, ctx=None):
     d_x = _to_device(x)
     d_idx, d_dist, _ = knn_device(ctx, d_x, n_neighbors)
     indptr, indices, data, _, _ = fuzzy_simplicial_set_device(ctx, d_idx, d_dist, n, n_neighbors)
-    ip, h_data, h_indices, h_idx, h_dist = _to_host(indptr, data, indices, d_idx, d_dist)
+    # column 0 is the query itself by construction (knn_rescore_kernel / knn_fallback_kernel), cf. the reference's
+    # `_get_sparse_matrix_from_indices_distances(..., keep_self=False)` (src/scanpy/neighbors/_common.py:35-61)
+    nb_idx = d_idx[:, 1:].contiguous().view(-1)
+    nb_dist = d_dist[:, 1:].contiguous().view(-1)
+    ip, h_data, h_indices, h_nb_idx, h_nb_dist = _to_host(indptr, data, indices, nb_idx, nb_dist)
     conn = sparse.csr_matrix((h_data, h_indices, ip if ip[-1] >= 2**31 else ip.astype(np.int32)), shape=(n, n))
-    return h_idx, h_dist, conn
+    km1 = n_neighbors - 1
+    it = np.int64 if n * km1 >= 2**31 else np.int32
+    dist_indptr = np.arange(0, n * km1 + 1, km1, dtype=it) if km1 > 0 else np.zeros(n + 1, it)
+    dist = sparse.csr_matrix((h_nb_dist, h_nb_idx, dist_indptr), shape=(n, n))
+    return dist, conn
 
 
 def leiden_device(ctx, d_indptr, d_indices, d_weights, n: int, *, resolution: float = 1.0, n_iterations: int = -1,

@@ -230,16 +230,21 @@ __device__ __forceinline__ bool lex_less(double ka, int ia, double kb, int ib) {
 // R = proposals per lane: the list has 32*R entries (R = 1: 32 proposals, k <= 24 keeps a slack of >= 8;
 // R = 2: 64 proposals for k up to 56)
 template <int R>
-__global__ void knn_rescore_kernel(const float* __restrict__ X, int64_t n_points, int d, int64_t q0, int64_t n_query,
+__global__ void knn_rescore_kernel(const float* __restrict__ X, int64_t n_points, int d, int64_t q0, int64_t ql_base,
+                                   const int32_t* __restrict__ row_map, int64_t n_rows,
                                    int k, const float* __restrict__ cand_score, const int32_t* __restrict__ cand_idx,
                                    const unsigned int* __restrict__ maxnorm_bits, const float* __restrict__ inv_s2,
-                                   double eps_coef, int32_t* __restrict__ idx_out,
+                                   double c_q, double c_n, const float* __restrict__ dnorm,
+                                   const unsigned int* __restrict__ dmax_bits, int32_t* __restrict__ idx_out,
                                    double* __restrict__ dist_out, int32_t* __restrict__ work_q,
                                    double* __restrict__ work_ub, unsigned long long* __restrict__ work_cnt) {
   constexpr int LM = 32 * R;
   const int lane = threadIdx.x & 31;
-  const int64_t ql = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (ql >= n_query) return;
+  // launch row i holds the proposals of local query ql (= row_map[i] for a gathered re-sweep, else ql_base + i);
+  // outputs and queue entries are indexed by ql, the point itself is q0 + ql
+  const int64_t li = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (li >= n_rows) return;
+  const int64_t ql = row_map ? (int64_t)row_map[li] : ql_base + li;
   const int64_t q = q0 + ql;
   const float* xq = X + q * d;
   double key[R];
@@ -249,8 +254,8 @@ __global__ void knn_rescore_kernel(const float* __restrict__ X, int64_t n_points
   bool all_used = true;
 #pragma unroll
   for (int r = 0; r < R; ++r) {
-    const int32_t ci = cand_idx[ql * LM + r * 32 + lane];
-    const float cs = cand_score[ql * LM + r * 32 + lane];
+    const int32_t ci = cand_idx[li * LM + r * 32 + lane];
+    const float cs = cand_score[li * LM + r * 32 + lane];
     const float* xc = X + (int64_t)(ci < 0 ? 0 : ci) * d;
     double acc = 0.0, qq = 0.0;
     for (int j = 0; j < d; ++j) {
@@ -262,7 +267,8 @@ __global__ void knn_rescore_kernel(const float* __restrict__ X, int64_t n_points
     qn = qq;
     key[r] = ci < 0 ? DBL_MAX : ((ci == q) ? -1.0 : acc);
     id[r] = ci < 0 ? INT32_MAX : ci;
-    if (ci >= 0) smin = fminf(smin, cs); else all_used = false;
+    smin = fminf(smin, cs);  // unused slots hold the sweep's starting threshold (-inf for a cold start)
+    if (ci < 0) all_used = false;
   }
   // bitonic sort of the 32*R elements (element e = r*32 + lane) ascending by (key, id)
 #pragma unroll
@@ -302,11 +308,15 @@ __global__ void knn_rescore_kernel(const float* __restrict__ X, int64_t n_points
   for (int o = 16; o > 0; o >>= 1) smin = fminf(smin, __shfl_xor_sync(0xffffffffu, smin, o));
   const bool list_full = __all_sync(0xffffffffu, all_used);
   bool certified;
-  if (!list_full) {
-    certified = true;  // fewer than 32*R points exist: the proposal list is the whole data set
+  if (!list_full && smin == -INFINITY) {
+    certified = true;  // cold start and fewer than 32*R points exist: the proposal list is the whole data set
   } else {
     const double Rn = sqrt((double)__uint_as_float(*maxnorm_bits));
-    const double eps = eps_coef * (0.5 * Rn * Rn + sqrt(qn) * Rn);
+    double eps = c_n * 0.5 * Rn * Rn + c_q * sqrt(qn) * Rn;
+    if (dnorm) {  // fp16 tier: |q.c - q_hi.c_hi| <= |dq| R + (|q| + |dq|) max|dc|
+      const double dq = (double)dnorm[q], dc = (double)__uint_as_float(*dmax_bits);
+      eps += (dq * Rn + (sqrt(qn) + dq) * dc) * (1.0 + 1e-6);
+    }
     const double bound = qn - 2.0 * ((double)smin * (inv_s2 ? (double)*inv_s2 : 1.0) + eps);
     certified = self_first && (kth < bound);
   }
@@ -414,11 +424,77 @@ knn_fallback_kernel(const float* __restrict__ X, const float* __restrict__ Xt, i
 
 }  // namespace
 
+namespace {
+
+struct EventPairs {  // CUDA-event brackets around the sweep kernels of one call (info != NULL only)
+  cudaEvent_t ev[8][2];
+  int n = 0;
+  bool on = false;
+  cudaStream_t st = nullptr;
+  int32_t begin() {
+    if (!on || n >= 8) return SB2_OK;
+    SB2_CUDA(cudaEventCreate(&ev[n][0]));
+    SB2_CUDA(cudaEventCreate(&ev[n][1]));
+    SB2_CUDA(cudaEventRecord(ev[n][0], st));
+    return SB2_OK;
+  }
+  int32_t end() {
+    if (!on || n >= 8) return SB2_OK;
+    SB2_CUDA(cudaEventRecord(ev[n][1], st));
+    ++n;
+    return SB2_OK;
+  }
+  float total_ms() {
+    float t = 0.0f;
+    for (int i = 0; i < n; ++i) {
+      float ms = 0.0f;
+      if (cudaEventElapsedTime(&ms, ev[i][0], ev[i][1]) == cudaSuccess) t += ms;
+    }
+    return t;
+  }
+  ~EventPairs() {
+    for (int i = 0; i < n; ++i) { cudaEventDestroy(ev[i][0]); cudaEventDestroy(ev[i][1]); }
+  }
+};
+
+int32_t launch_rescore(sb2_ctx* ctx, int list_m, const float* d_x, int64_t n_points, int d, int64_t q0, int64_t ql_base,
+                       const int32_t* row_map, int64_t n_rows, int k, const float* cand_score, const int32_t* cand_idx,
+                       const unsigned int* maxnorm, const float* inv_s2, double c_q, double c_n, const float* dnorm,
+                       const unsigned int* dmax_bits, int32_t* d_idx,
+                       double* d_dist, int32_t* wq, double* wub, unsigned long long* wcnt) {
+  if (n_rows == 0) return SB2_OK;
+  const int wpb = 8;
+  const unsigned grid = (unsigned)ceil_div64(n_rows, wpb);
+  if (list_m == 32)
+    knn_rescore_kernel<1><<<grid, wpb * 32, 0, ctx->stream>>>(d_x, n_points, d, q0, ql_base, row_map, n_rows, k, cand_score,
+                                                               cand_idx, maxnorm, inv_s2, c_q, c_n, dnorm, dmax_bits, d_idx, d_dist, wq, wub, wcnt);
+  else
+    knn_rescore_kernel<2><<<grid, wpb * 32, 0, ctx->stream>>>(d_x, n_points, d, q0, ql_base, row_map, n_rows, k, cand_score,
+                                                               cand_idx, maxnorm, inv_s2, c_q, c_n, dnorm, dmax_bits, d_idx, d_dist, wq, wub, wcnt);
+  SB2_LAUNCH_CHECK(ctx);
+  return SB2_OK;
+}
+
+int32_t read_count(sb2_ctx* ctx, const unsigned long long* d_cnt, int64_t* out) {
+  unsigned long long h = 0;
+  SB2_CUDA(cudaMemcpyAsync(&h, d_cnt, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
+  SB2_CUDA(cudaStreamSynchronize(ctx->stream));
+  *out = (int64_t)h;
+  return SB2_OK;
+}
+
+}  // namespace
+
+// Exact kNN.  Tensor path (default), in tiers that each end in the same fp64 re-score + certificate:
+//   tier 1  one fp16 sweep (K = d+3): proposals whose rounding bound (2^-10 |q| R) still certifies the exact top-k are final
+//   tier 2  rows tier 1 could not certify are gathered and swept again in split precision (K = 3d+3, bound ~2^-16 |q| R)
+//   tier 3  rows still open (exact ties at the k-th distance, floods of duplicates): fp64 scan of every point
+// A pilot of one wave of CTAs measures tier 1's certification rate; if most rows fail (data far from the origin,
+// tiny neighbour gaps) the remaining rows go straight to the split-precision sweep.
 extern "C" int32_t sb2_knn_l2_f32(sb2_ctx* ctx, int64_t n_points, int32_t d, const float* d_x, int64_t q0,
                                   int64_t n_query, int32_t k, int32_t* d_idx, double* d_dist, sb2_knn_info* info) {
   SB2_CHECK_ARG(ctx && d_x && d_idx && d_dist, "null pointer");
   SB2_CHECK_ARG(n_points >= 1 && n_points < (int64_t)INT32_MAX - TILE, "n_points");
-  // a query tile + two candidate stages of (d+1)*512 B must fit the 227 KB of shared memory
   SB2_CHECK_ARG(d >= 1 && d <= 150, "d must be in [1,150]");
   SB2_CHECK_ARG(k >= 1 && k <= 56 && k <= n_points, "k must be in [1,56] and <= n_points");
   SB2_CHECK_ARG(q0 >= 0 && n_query >= 0 && q0 + n_query <= n_points, "query range");
@@ -433,50 +509,122 @@ extern "C" int32_t sb2_knn_l2_f32(sb2_ctx* ctx, int64_t n_points, int32_t d, con
   unsigned int* maxnorm;
   float* cand_score;
   int32_t* cand_idx;
-  int32_t* work_q;
-  double* work_ub;
-  unsigned long long* work_cnt;
+  int32_t *wq1, *wq2;
+  double *wub1, *wub2;
+  unsigned long long* wcnt;  // [0] rows tier 1 left open, [1] rows for the exact scan
   SB2_TRY(scr.alloc(&Xt, (size_t)(n_tiles * chunk_f)));
   SB2_TRY(scr.alloc(&maxnorm, 4));
   // 32 proposals per query keep a slack of >= 8 behind k <= 24; larger k gets 64 (tensor path only: the FFMA pass
-  // keeps one proposal per lane, its rows then lean on the exact fallback)
+  // keeps one proposal per lane, its rows then lean on the exact scan)
   const char* force = getenv("SB2_KNN_PASS1");
+  const char* tiers = getenv("SB2_KNN_TIERS");
   const bool use_tc = knn_tc_supported(d) && !(force && strcmp(force, "ffma") == 0);
-  const int list_m = (use_tc && k > 24) ? 64 : 32;
+  const bool split_only = tiers && strcmp(tiers, "3") == 0;
+  const char* list_env = getenv("SB2_KNN_LIST");
+  const int list_m = (use_tc && (k > 24 || (list_env && strcmp(list_env, "64") == 0))) ? 64 : 32;
   SB2_CHECK_ARG(k <= list_m - 2, "k > 30 needs the tensor-core pass (SB2_KNN_PASS1=ffma limits k to 30)");
   SB2_TRY(scr.alloc(&cand_score, (size_t)n_query * list_m));
   SB2_TRY(scr.alloc(&cand_idx, (size_t)n_query * list_m));
-  SB2_TRY(scr.alloc(&work_q, (size_t)n_query));
-  SB2_TRY(scr.alloc(&work_ub, (size_t)n_query));
-  SB2_TRY(scr.alloc(&work_cnt, 2));
+  SB2_TRY(scr.alloc(&wq1, (size_t)n_query));
+  SB2_TRY(scr.alloc(&wub1, (size_t)n_query));
+  SB2_TRY(scr.alloc(&wq2, (size_t)n_query));
+  SB2_TRY(scr.alloc(&wub2, (size_t)n_query));
+  SB2_TRY(scr.alloc(&wcnt, 2));
   SB2_CUDA(cudaMemsetAsync(maxnorm, 0, 16, st));
-  SB2_CUDA(cudaMemsetAsync(work_cnt, 0, 16, st));
-
+  SB2_CUDA(cudaMemsetAsync(wcnt, 0, 16, st));
   {
     size_t smem = (size_t)TILE * d * sizeof(float);
     SB2_CUDA(cudaFuncSetAttribute(knn_prep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     knn_prep_kernel<<<(unsigned)n_tiles, 256, smem, st>>>(d_x, n_points, d, Xt, maxnorm);
     SB2_LAUNCH_CHECK(ctx);
   }
-  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-  if (info) {
-    SB2_CUDA(cudaEventCreate(&ev0));
-    SB2_CUDA(cudaEventCreate(&ev1));
-  }
-  double issued_flops = 2.0 * (double)n_query * (double)n_points * (double)d;
-  // pass 1: tensor-core split-precision sweep (knn_tc.cu) when the concatenated K axis fits, else fp32 FFMA
-  float* inv_s2 = nullptr;
-  double eps_coef = 1.5 * (double)(d + 2) * 5.9604644775390625e-08;
+  EventPairs evs;
+  evs.on = info != nullptr;
+  evs.st = st;
+  double issued_flops = 0.0;
+  int64_t n_resweep = 0;
   if (use_tc) {
+    KnnTcShape sh1, sh3;
+    SB2_CHECK_ARG(knn_tc_shape(ctx, d, 1, &sh1) && knn_tc_shape(ctx, d, 3, &sh3), "tensor-core kNN tile does not fit shared memory");
+    float* inv_s2;
     SB2_TRY(scr.alloc(&inv_s2, 4));
-    SB2_TRY(knn_tc_pass1(ctx, scr, d_x, n_points, d, maxnorm, q0, n_query, list_m, cand_score, cand_idx, inv_s2, &eps_coef,
-                         ev0, &issued_flops));
+    double cq1, cn1, cq3, cn3;
+    knn_tc_error_coefs(sh1, &cq1, &cn1);
+    knn_tc_error_coefs(sh3, &cq3, &cn3);
+    __half *A1 = nullptr, *B1 = nullptr, *A3 = nullptr, *B3 = nullptr;
+    float* dnorm = nullptr;  // |x - fp16(x)| per point; its maximum lives in maxnorm[1]
+    const int64_t qt0 = q0 / TILE;
+    int64_t done = 0;  // local rows [0, done) have been through their first sweep
+    bool direct_split = split_only;
+    if (!split_only) {
+      SB2_TRY(scr.alloc(&A1, knn_tc_image_halves(sh1, n_points)));
+      SB2_TRY(scr.alloc(&B1, knn_tc_image_halves(sh1, n_points)));
+      SB2_TRY(scr.alloc(&dnorm, (size_t)n_points));
+      SB2_TRY(knn_tc_build_images(ctx, sh1, d_x, n_points, d, maxnorm, nullptr, 0, A1, B1, inv_s2, dnorm, maxnorm + 1));
+      // pilot: one wave of CTAs
+      const int64_t wave = (int64_t)ctx->prop.multiProcessorCount * sh1.qh * TILE;
+      const int64_t first = n_query >= 4 * wave ? wave : n_query;
+      SB2_TRY(evs.begin());
+      SB2_TRY(knn_tc_sweep(ctx, sh1, A1, qt0, B1, n_points, first, list_m, cand_score, cand_idx, &issued_flops));
+      SB2_TRY(evs.end());
+      SB2_TRY(launch_rescore(ctx, list_m, d_x, n_points, d, q0, 0, nullptr, first, k, cand_score, cand_idx, maxnorm, inv_s2, cq1,
+                             cn1, dnorm, maxnorm + 1, d_idx, d_dist, wq1, wub1, wcnt));
+      done = first;
+      if (first < n_query) {
+        int64_t open1 = 0;
+        SB2_TRY(read_count(ctx, wcnt, &open1));
+        direct_split = open1 * 2 > first;
+        if (!direct_split) {
+          const int64_t rest = n_query - done;
+          SB2_TRY(evs.begin());
+          SB2_TRY(knn_tc_sweep(ctx, sh1, A1, qt0 + done / TILE, B1, n_points, rest, list_m, cand_score + done * list_m,
+                               cand_idx + done * list_m, &issued_flops));
+          SB2_TRY(evs.end());
+          SB2_TRY(launch_rescore(ctx, list_m, d_x, n_points, d, q0, done, nullptr, rest, k, cand_score + done * list_m,
+                                 cand_idx + done * list_m, maxnorm, inv_s2, cq1, cn1, dnorm, maxnorm + 1, d_idx, d_dist, wq1, wub1, wcnt));
+          done = n_query;
+        }
+      }
+    }
+    if (done < n_query) {
+      // split-precision sweep of the remaining rows, straight from the full image arrays
+      SB2_TRY(scr.alloc(&A3, knn_tc_image_halves(sh3, n_points)));
+      SB2_TRY(scr.alloc(&B3, knn_tc_image_halves(sh3, n_points)));
+      SB2_TRY(knn_tc_build_images(ctx, sh3, d_x, n_points, d, maxnorm, nullptr, 0, A3, B3, inv_s2));
+      const int64_t rest = n_query - done;
+      SB2_TRY(evs.begin());
+      SB2_TRY(knn_tc_sweep(ctx, sh3, A3, qt0 + done / TILE, B3, n_points, rest, list_m, cand_score + done * list_m,
+                           cand_idx + done * list_m, &issued_flops));
+      SB2_TRY(evs.end());
+      SB2_TRY(launch_rescore(ctx, list_m, d_x, n_points, d, q0, done, nullptr, rest, k, cand_score + done * list_m,
+                             cand_idx + done * list_m, maxnorm, inv_s2, cq3, cn3, nullptr, nullptr, d_idx, d_dist, wq2, wub2, wcnt + 1));
+    }
+    if (!split_only) {
+      // tier 2: gather the rows tier 1 left open and sweep them in split precision
+      SB2_TRY(read_count(ctx, wcnt, &n_resweep));
+      if (n_resweep > 0) {
+        if (!B3) {
+          SB2_TRY(scr.alloc(&B3, knn_tc_image_halves(sh3, n_points)));
+          SB2_TRY(knn_tc_build_images(ctx, sh3, d_x, n_points, d, maxnorm, nullptr, 0, nullptr, B3, inv_s2));
+        }
+        __half* Ag;
+        SB2_TRY(scr.alloc(&Ag, knn_tc_image_halves(sh3, n_resweep)));
+        SB2_TRY(knn_tc_build_images(ctx, sh3, d_x, n_resweep, d, maxnorm, wq1, q0, Ag, nullptr, inv_s2));
+        SB2_TRY(evs.begin());
+        SB2_TRY(knn_tc_sweep(ctx, sh3, Ag, 0, B3, n_points, n_resweep, list_m, cand_score, cand_idx, &issued_flops));
+        SB2_TRY(evs.end());
+        SB2_TRY(launch_rescore(ctx, list_m, d_x, n_points, d, q0, 0, wq1, n_resweep, k, cand_score, cand_idx, maxnorm, inv_s2, cq3,
+                               cn3, nullptr, nullptr, d_idx, d_dist, wq2, wub2, wcnt + 1));
+      }
+    }
   } else {
-    if (ev0) SB2_CUDA(cudaEventRecord(ev0, st));
+    issued_flops = 2.0 * (double)n_query * (double)n_points * (double)d;
+    const double c = 1.5 * (double)(d + 2) * 5.9604644775390625e-08;
     const int64_t q_tiles = ceil_div64(n_query, TILE);
     const size_t chunk_b = (size_t)chunk_f * 4;
     const size_t smem3 = chunk_b * 4 + 64, smem2 = chunk_b * 3 + 64;
     const size_t lim = ctx->prop.sharedMemPerBlockOptin;
+    SB2_TRY(evs.begin());
     if (smem3 <= lim) {
       SB2_CUDA(cudaFuncSetAttribute(knn_pass1_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem3));
       knn_pass1_kernel<3><<<(unsigned)q_tiles, PASS1_THREADS, smem3, st>>>(Xt, d, n_tiles, q0 / TILE, n_query,
@@ -488,44 +636,30 @@ extern "C" int32_t sb2_knn_l2_f32(sb2_ctx* ctx, int64_t n_points, int32_t d, con
                                                                            cand_score, cand_idx);
     }
     SB2_LAUNCH_CHECK(ctx);
-  }
-  if (info) SB2_CUDA(cudaEventRecord(ev1, st));
-  {
-    const int wpb = 8;
-    if (list_m == 32)
-      knn_rescore_kernel<1><<<(unsigned)ceil_div64(n_query, wpb), wpb * 32, 0, st>>>(
-          d_x, n_points, d, q0, n_query, k, cand_score, cand_idx, maxnorm, inv_s2, eps_coef, d_idx, d_dist, work_q, work_ub,
-          work_cnt);
-    else
-      knn_rescore_kernel<2><<<(unsigned)ceil_div64(n_query, wpb), wpb * 32, 0, st>>>(
-          d_x, n_points, d, q0, n_query, k, cand_score, cand_idx, maxnorm, inv_s2, eps_coef, d_idx, d_dist, work_q, work_ub,
-          work_cnt);
-    SB2_LAUNCH_CHECK(ctx);
+    SB2_TRY(evs.end());
+    SB2_TRY(launch_rescore(ctx, list_m, d_x, n_points, d, q0, 0, nullptr, n_query, k, cand_score, cand_idx, maxnorm, nullptr, c, c,
+                           nullptr, nullptr, d_idx, d_dist, wq2, wub2, wcnt + 1));
   }
   {
     const int grid = ctx->prop.multiProcessorCount * 4;
-    knn_fallback_kernel<<<grid, FB_THREADS, 0, st>>>(d_x, Xt, n_points, d, q0, k, work_q, work_ub, work_cnt, d_idx,
-                                                     d_dist);
+    knn_fallback_kernel<<<grid, FB_THREADS, 0, st>>>(d_x, Xt, n_points, d, q0, k, wq2, wub2, wcnt + 1, d_idx, d_dist);
     SB2_LAUNCH_CHECK(ctx);
   }
   if (info) {
     unsigned long long h_cnt = 0;
     unsigned int h_bits = 0;
-    SB2_CUDA(cudaMemcpyAsync(&h_cnt, work_cnt, sizeof(h_cnt), cudaMemcpyDeviceToHost, st));
+    SB2_CUDA(cudaMemcpyAsync(&h_cnt, wcnt + 1, sizeof(h_cnt), cudaMemcpyDeviceToHost, st));
     SB2_CUDA(cudaMemcpyAsync(&h_bits, maxnorm, sizeof(h_bits), cudaMemcpyDeviceToHost, st));
     SB2_CUDA(cudaStreamSynchronize(st));
     info->n_uncertified = (int64_t)h_cnt;
     float f;
     memcpy(&f, &h_bits, 4);
     info->max_norm = sqrtf(f);
-    float ms = 0.0f;
-    SB2_CUDA(cudaEventElapsedTime(&ms, ev0, ev1));
-    info->pass1_ms = ms;
+    info->pass1_ms = evs.total_ms();
     info->pass1_flops = 2.0 * (double)n_query * (double)n_points * (double)d;
     info->pass1_issued_flops = issued_flops;
     info->pass1_tensor = use_tc ? 1 : 0;
-    cudaEventDestroy(ev0);
-    cudaEventDestroy(ev1);
+    info->n_resweep = n_resweep;
   }
   return SB2_OK;
 }

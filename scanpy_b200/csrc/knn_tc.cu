@@ -34,8 +34,8 @@
 namespace {
 
 constexpr int TM = 128;           // rows per operand tile (UMMA M and N)
-constexpr int LISTM = 32;
-constexpr int NSTAGE = 3;
+constexpr int MAXST = 8;          // upper bound of the candidate ring depth (runtime nstage <= MAXST)
+constexpr int BAR_BYTES = 256;    // mbarriers + TMEM slot behind the ring
 constexpr int TC_THREADS = 320;   // 10 warps
 constexpr uint32_t SBO = 128;     // bytes between 8-row groups (core matrices contiguous)
 constexpr uint32_t LBO = TM * 16; // bytes between K-chunks (8 fp16) : [kc][row-group][8][8]
@@ -119,21 +119,38 @@ __device__ __forceinline__ float tc_scale_from_maxnorm(unsigned int maxnorm_bits
 }
 
 __global__ void __launch_bounds__(256)
-knn_tc_prep_kernel(const float* __restrict__ X, int64_t n, int d, int kpad, const unsigned int* __restrict__ maxnorm_bits,
-                   __half* __restrict__ Aimg, __half* __restrict__ Bimg, float* __restrict__ inv_s2) {
+knn_tc_prep_kernel(const float* __restrict__ X, int64_t n, int d, int kpad, int terms,
+                   const unsigned int* __restrict__ maxnorm_bits, const int32_t* __restrict__ gather, int64_t gather_base,
+                   __half* __restrict__ Aimg, __half* __restrict__ Bimg, float* __restrict__ inv_s2,
+                   float* __restrict__ dnorm, unsigned int* __restrict__ dmax_bits) {
+  // dnorm[p] (optional) = |x_p - fp16(x_p)| in the units of X, rounded up; *dmax_bits = its maximum (float bits)
+  // terms = 3: A = [hi | hi | lo | 1 1 1], B = [hi | lo | hi | h0 h1 h2]   (22-bit operands)
+  // terms = 1: A = [hi | 1 1 1],           B = [hi | h0 h1 h2]             (11-bit operands, the fast first tier)
+  // gather != nullptr: image row r of tile t is point gather_base + gather[t*128 + r] (rows past n are zero rows);
+  // Aimg / Bimg may each be null (that image is not written)
   const int64_t t = blockIdx.x;
   const float s = tc_scale_from_maxnorm(*maxnorm_bits);
   if (t == 0 && threadIdx.x == 0) *inv_s2 = 1.0f / (s * s);
   __shared__ __half hn3[TM][3];
   // per-row -|x|^2 s^2 / 2, three-way fp16 split
+  const int kd = terms * d;  // coordinates on the K axis before the three norm slots
   if (threadIdx.x < TM) {
     const int64_t p = t * TM + threadIdx.x;
     __half h0 = __float2half_rn(-60000.0f), h1 = __float2half_rn(0.0f), h2 = __float2half_rn(0.0f);
     if (p < n) {
-      double acc = 0.0;
+      double acc = 0.0, dacc = 0.0;
+      const int64_t ps = gather ? gather_base + gather[p] : p;
       for (int k = 0; k < d; ++k) {
-        const double v = (double)X[p * d + k] * (double)s;
+        const float xs = X[ps * d + k] * s;
+        const double v = (double)xs;
         acc += v * v;
+        const double dl = v - (double)__half2float(__float2half_rn(xs));
+        dacc += dl * dl;
+      }
+      if (dnorm) {
+        const float dn = __double2float_ru(sqrt(dacc) * (1.0 + 1e-12) / (double)s);
+        dnorm[p] = dn;
+        atomicMax(dmax_bits, __float_as_uint(dn));
       }
       const double hn = -0.5 * acc;
       h0 = __float2half_rn((float)hn);
@@ -146,11 +163,12 @@ knn_tc_prep_kernel(const float* __restrict__ X, int64_t n, int d, int kpad, cons
   __syncthreads();
   const int nkc = kpad / 8;
   const size_t img = (size_t)TM * kpad;  // halves per image
-  __half* Aout = Aimg + (size_t)t * img;
-  __half* Bout = Bimg + (size_t)t * img;
+  __half* Aout = Aimg ? Aimg + (size_t)t * img : nullptr;
+  __half* Bout = Bimg ? Bimg + (size_t)t * img : nullptr;
   for (int i = threadIdx.x; i < TM * nkc; i += blockDim.x) {
     const int kc = i / TM, r = i % TM;
     const int64_t p = t * TM + r;
+    const int64_t ps = (gather && p < n) ? gather_base + gather[p] : p;
     __align__(16) __half a8[8];
     __align__(16) __half b8[8];
 #pragma unroll
@@ -158,25 +176,25 @@ knn_tc_prep_kernel(const float* __restrict__ X, int64_t n, int d, int kpad, cons
       const int e = kc * 8 + j;
       __half av = __float2half_rn(0.0f), bv = av;
       if (p < n) {
-        if (e < 3 * d) {
+        if (e < kd) {
           const int seg = e / d, k = e - seg * d;
-          const float xs = X[p * d + k] * s;
+          const float xs = X[ps * d + k] * s;
           const __half hi = __float2half_rn(xs);
           const __half lo = __float2half_rn(xs - __half2float(hi));
           av = seg == 2 ? lo : hi;   // A = [hi | hi | lo]
           bv = seg == 1 ? lo : hi;   // B = [hi | lo | hi]
-        } else if (e < 3 * d + 3) {
+        } else if (e < kd + 3) {
           av = __float2half_rn(1.0f);
-          bv = hn3[r][e - 3 * d];
+          bv = hn3[r][e - kd];
         }
-      } else if (e == 3 * d) {
+      } else if (e == kd) {
         bv = hn3[r][0];  // padding candidates: score -60000 (padding queries are all-zero rows)
       }
       a8[j] = av; b8[j] = bv;
     }
     const size_t off = ((size_t)kc * LBO + (size_t)(r >> 3) * SBO + (size_t)(r & 7) * 16) / 2;  // in halves
-    *reinterpret_cast<uint4*>(Aout + off) = *reinterpret_cast<const uint4*>(a8);
-    *reinterpret_cast<uint4*>(Bout + off) = *reinterpret_cast<const uint4*>(b8);
+    if (Aout) *reinterpret_cast<uint4*>(Aout + off) = *reinterpret_cast<const uint4*>(a8);
+    if (Bout) *reinterpret_cast<uint4*>(Bout + off) = *reinterpret_cast<const uint4*>(b8);
   }
 }
 
@@ -221,33 +239,61 @@ __device__ __forceinline__ void list_insert(RowList<NG>& L, int32_t* __restrict_
   for (int g = 1; g < NG; ++g) t = fminf(t, L.gm[g]);
   L.tau = t;
 }
-// examine one 32-column chunk of the row (values already in registers).  Fast path: a 3-input max tree and
-// one compare.  Rare path (about 340 times per row over a 1.3M sweep): pull out the chunk's maxima one by one
-// while they still beat tau.  Only ONE copy of the insertion code exists per call site (the while loop), so
-// the kernel stays small enough for the instruction caches.
-__device__ __forceinline__ float max32(const uint32_t (&v)[32]) {
-  float m = __uint_as_float(v[0]);
-#pragma unroll
-  for (int j = 1; j < 32; ++j) m = fmaxf(m, __uint_as_float(v[j]));
-  return m;
+// examine one 32-column chunk of the row (values already in registers).  Fast path: a two-level 3-input max
+// tree (four independent quarter maxima, so the FMNMX3 latencies overlap) and one compare.  Rare path (about
+// 340 times per row over a 1.3M sweep): visit the quarters whose maximum beats tau, copy the quarter's eight
+// values aside and pull its maxima out one by one.  The quarter loop is NOT unrolled: one copy of the extraction
+// and insertion code per call site keeps the kernel inside the instruction caches.
+__device__ __forceinline__ float fmax3(float a, float b, float c) {
+  float d;
+  asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
+  return d;
+}
+__device__ __forceinline__ float max8u(const uint32_t* v) {
+  return fmax3(fmax3(__uint_as_float(v[0]), __uint_as_float(v[1]), __uint_as_float(v[2])),
+               fmax3(__uint_as_float(v[3]), __uint_as_float(v[4]), __uint_as_float(v[5])),
+               fmaxf(__uint_as_float(v[6]), __uint_as_float(v[7])));
 }
 template <int NG>
-__device__ __forceinline__ void scan_chunk(RowList<NG>& L, int32_t* __restrict__ id, uint32_t (&v)[32], int32_t cand0,
+__device__ __forceinline__ void scan_chunk(RowList<NG>& L, int32_t* __restrict__ id, const uint32_t (&v)[32], int32_t cand0,
                                            int32_t n_points) {
-  float m = max32(v);
-  while (m > L.tau) {
-    int j = 0;
-    bool found = false;
-    const uint32_t mb = __float_as_uint(m);
+  const float h0 = max8u(&v[0]), h1 = max8u(&v[8]), h2 = max8u(&v[16]), h3 = max8u(&v[24]);
+  if (fmaxf(fmax3(h0, h1, h2), h3) > L.tau) {
+#pragma unroll 1
+    for (int q = 0; q < 4; ++q) {
+      float hq = q == 0 ? h0 : (q == 1 ? h1 : (q == 2 ? h2 : h3));
+      if (hq > L.tau) {
+        uint32_t w[8];
 #pragma unroll
-    for (int jj = 0; jj < 32; ++jj) {
-      const bool hset = !found && (v[jj] == mb);
-      j = hset ? jj : j;
-      v[jj] = hset ? 0xff800000u : v[jj];  // knock the maximum out (-inf)
-      found |= hset;
+        for (int i = 0; i < 8; ++i) w[i] = q == 0 ? v[i] : (q == 1 ? v[8 + i] : (q == 2 ? v[16 + i] : v[24 + i]));
+        do {
+          int j = 0;
+          bool found = false;
+          const uint32_t mb = __float_as_uint(hq);
+#pragma unroll
+          for (int jj = 0; jj < 8; ++jj) {
+            const bool hset = !found && (w[jj] == mb);
+            j = hset ? jj : j;
+            w[jj] = hset ? 0xff800000u : w[jj];  // knock the maximum out (-inf)
+            found |= hset;
+          }
+          const int32_t cand = cand0 + q * 8 + j;
+          if (cand < n_points) list_insert(L, id, hq, cand);
+          hq = max8u(w);
+        } while (hq > L.tau);
+      }
     }
-    if (cand0 + j < n_points) list_insert(L, id, m, cand0 + j);
-    m = max32(v);
+  }
+}
+constexpr int EST_R = 6;
+// estimate phase: keep the EST_R largest chunk maxima (sorted descending), branch-free
+__device__ __forceinline__ void est_chunk(float (&est)[EST_R], const uint32_t (&v)[32]) {
+  float cm = fmaxf(fmax3(max8u(&v[0]), max8u(&v[8]), max8u(&v[16])), max8u(&v[24]));
+#pragma unroll
+  for (int i = 0; i < EST_R; ++i) {
+    const float hi = fmaxf(est[i], cm);
+    cm = fminf(est[i], cm);
+    est[i] = hi;
   }
 }
 __device__ __forceinline__ void tmem_ld32_nowait(uint32_t taddr, uint32_t (&v)[32]) {
@@ -265,25 +311,27 @@ __device__ __forceinline__ void tmem_ld32_nowait(uint32_t taddr, uint32_t (&v)[3
 // staged in (1 when a whole image fits a ring stage; 2 or 4 for wide embeddings, d up to 150).
 template <int NG, int QH>
 __global__ void __launch_bounds__(TC_THREADS, 1)
-knn_pass1_tc_kernel(const __half* __restrict__ Aimg, const __half* __restrict__ Bimg, int kpad, int nsplit, int64_t n_btiles,
+knn_pass1_tc_kernel(const __half* __restrict__ Aimg, const __half* __restrict__ Bimg, int kpad, int nsplit, int nstage, int64_t n_btiles,
+                    int64_t n_est, int64_t est_stride,
                     int64_t qtile0, int64_t n_query, int32_t n_points, float* __restrict__ cand_score,
                     int32_t* __restrict__ cand_idx) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   const uint32_t tile_b = (uint32_t)TM * (uint32_t)kpad * 2u;  // bytes per 128-row image
   const uint32_t part_b = tile_b / (uint32_t)nsplit;  // bytes per staged K-slice of a candidate image
   unsigned char* As = smem_raw;                     // QH images (128*QH queries)
-  unsigned char* Bs0 = smem_raw + QH * tile_b;      // NSTAGE slices
-  uint64_t* bars = reinterpret_cast<uint64_t*>(Bs0 + (size_t)NSTAGE * part_b);
-  uint64_t* full = bars;                  // [NSTAGE] producer -> MMA
-  uint64_t* empty = bars + NSTAGE;        // [NSTAGE] MMA (commit) -> producer
-  uint64_t* afull = bars + 2 * NSTAGE;    // [1]
-  uint64_t* tfull = bars + 2 * NSTAGE + 1;   // [2] MMA (commit) -> epilogue
-  uint64_t* tempty = bars + 2 * NSTAGE + 3;  // [2] epilogue -> MMA
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * NSTAGE + 5);
+  unsigned char* Bs0 = smem_raw + QH * tile_b;      // nstage slices
+  uint64_t* bars = reinterpret_cast<uint64_t*>(Bs0 + (size_t)nstage * part_b);
+  uint64_t* full = bars;                  // [MAXST] producer -> MMA
+  uint64_t* empty = bars + MAXST;         // [MAXST] MMA (commit) -> producer
+  uint64_t* afull = bars + 2 * MAXST;     // [1]
+  uint64_t* tfull = bars + 2 * MAXST + 1;    // [2] MMA (commit) -> epilogue
+  uint64_t* tempty = bars + 2 * MAXST + 3;   // [2] epilogue -> MMA
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * MAXST + 5);
+  static_assert((2 * MAXST + 5) * 8 + 4 <= BAR_BYTES, "barrier block");
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
-    for (int s = 0; s < NSTAGE; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    for (int s = 0; s < nstage; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
     mbar_init(afull, 1);
     for (int b = 0; b < 2; ++b) { mbar_init(&tfull[b], 1); mbar_init(&tempty[b], 4 * QH); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -305,13 +353,18 @@ knn_pass1_tc_kernel(const __half* __restrict__ Aimg, const __half* __restrict__ 
       for (int h = 0; h < QH; ++h)
         bulk_g2s(As + (size_t)h * tile_b,
                  reinterpret_cast<const unsigned char*>(Aimg) + (size_t)(qtile0 + QH * (int64_t)blockIdx.x + h) * tile_b, tile_b, afull);
-      const int64_t n_it = n_btiles * nsplit;  // slices are contiguous in the image stream
-      for (int64_t it = 0; it < n_it; ++it) {
-        const int s = (int)(it % NSTAGE);
-        const int64_t use = it / NSTAGE;
-        if (use > 0) mbar_wait(&empty[s], (uint32_t)((use - 1) & 1));
-        mbar_expect_tx(&full[s], part_b);
-        bulk_g2s(Bs0 + (size_t)s * part_b, reinterpret_cast<const unsigned char*>(Bimg) + (size_t)it * part_b, part_b, &full[s]);
+      // visit order: n_est sample tiles (every est_stride-th) for the threshold estimate, then every tile
+      int64_t it = 0;
+      for (int64_t v = 0; v < n_est + n_btiles; ++v) {
+        const int64_t c = v < n_est ? v * est_stride : v - n_est;
+        for (int p = 0; p < nsplit; ++p, ++it) {
+          const int s = (int)(it % nstage);
+          const int64_t use = it / nstage;
+          if (use > 0) mbar_wait(&empty[s], (uint32_t)((use - 1) & 1));
+          mbar_expect_tx(&full[s], part_b);
+          bulk_g2s(Bs0 + (size_t)s * part_b, reinterpret_cast<const unsigned char*>(Bimg) + (size_t)c * tile_b + (size_t)p * part_b,
+                   part_b, &full[s]);
+        }
       }
     }
   } else if (warp == 1) {
@@ -320,12 +373,12 @@ knn_pass1_tc_kernel(const __half* __restrict__ Aimg, const __half* __restrict__ 
       mbar_wait(afull, 0);
       const uint32_t a_addr = smem_u32(As);
       int64_t it = 0;
-      for (int64_t c = 0; c < n_btiles; ++c) {
+      for (int64_t c = 0; c < n_est + n_btiles; ++c) {  // c counts visits here (the operands come through the ring)
         const int b = (int)(c & 1);
         const int64_t useb = c >> 1;
         for (int p = 0; p < nsplit; ++p, ++it) {
-          const int s = (int)(it % NSTAGE);
-          mbar_wait(&full[s], (uint32_t)((it / NSTAGE) & 1));
+          const int s = (int)(it % nstage);
+          mbar_wait(&full[s], (uint32_t)((it / nstage) & 1));
           if (p == 0 && useb > 0) mbar_wait(&tempty[b], (uint32_t)((useb - 1) & 1));
           tc_fence_after();
           const uint32_t b_addr = smem_u32(Bs0 + (size_t)s * part_b);
@@ -355,35 +408,59 @@ knn_pass1_tc_kernel(const __half* __restrict__ Aimg, const __half* __restrict__ 
     float* sc = cand_score + (valid ? ql : 0) * LM;
     int32_t* id = cand_idx + (valid ? ql : 0) * LM;
     RowList<NG> L;
-#pragma unroll
-    for (int i = 0; i < LM; ++i) L.ls[i] = -INFINITY;
-#pragma unroll
-    for (int g = 0; g < NG; ++g) L.gm[g] = -INFINITY;
-    L.tau = valid ? -INFINITY : INFINITY;  // rows past n_query never accept anything
+    L.tau = INFINITY;
     if (valid) {
 #pragma unroll
       for (int i = 0; i < LM; ++i) id[i] = -1;
     }
-    for (int64_t c = 0; c < n_btiles; ++c) {
+    // threshold estimate: the EST_R largest chunk maxima over the sample tiles.  The EST_R-th of them is, in
+    // expectation, the score of rank EST_R * est_stride among all candidates; the list starts "full" of sentinels
+    // at that score, so the sweep only ever handles the ~100 candidates per row that beat it (instead of the
+    // LM ln(n/LM) insertions of a cold start).  Any value is safe: the re-score certificate uses the final tau.
+    float est[EST_R];
+#pragma unroll
+    for (int i = 0; i < EST_R; ++i) est[i] = -INFINITY;
+    // software pipeline over the 32-column chunks of the accumulator slabs: the tcgen05.ld of chunk g+1 is in
+    // flight while chunk g is examined (two register buffers, va: even chunks, vb: odd chunks)
+    uint32_t va[32], vb[32];
+    const uint32_t lane_base = tmem_base + ((uint32_t)(lgrp * 32) << 16) + (uint32_t)(h * 128);
+    mbar_wait(&tfull[0], 0);
+    tc_fence_after();
+    tmem_ld32_nowait(lane_base, va);
+    const int64_t n_visit = n_est + n_btiles;
+    for (int64_t c = 0; c < n_visit; ++c) {
       const int b = (int)(c & 1);
-      mbar_wait(&tfull[b], (uint32_t)((c >> 1) & 1));
-      tc_fence_after();
-      const uint32_t tbase = tmem_base + ((uint32_t)(lgrp * 32) << 16) + (uint32_t)(b * (128 * QH) + h * 128);
-      const int32_t cbase = (int32_t)(c * TM);
+      const uint32_t tbase = lane_base + (uint32_t)(b * (128 * QH));
+      const bool estimating = c < n_est;
+      const int32_t cbase = (int32_t)((estimating ? 0 : c - n_est) * TM);
+      if (c == n_est) {
+        const float t0 = valid ? est[EST_R - 1] : INFINITY;  // rows past n_query never accept anything
+#pragma unroll
+        for (int i = 0; i < LM; ++i) L.ls[i] = t0;
+#pragma unroll
+        for (int g = 0; g < NG; ++g) L.gm[g] = t0;
+        L.tau = t0;
+      }
 #pragma unroll 1
-      for (int half = 0; half < 2; ++half) {
-        uint32_t va[32], vb[32];
-        tmem_ld32_nowait(tbase + (uint32_t)(half * 64), va);
-        tmem_ld32_nowait(tbase + (uint32_t)(half * 64 + 32), vb);
-        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-        if (half == 1) {
-          // the whole row slab has been read: hand the accumulator buffer back before examining the rest
+      for (int pair = 0; pair < 2; ++pair) {
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");  // va = chunk 2*pair
+        tmem_ld32_nowait(tbase + (uint32_t)(pair * 64 + 32), vb);
+        if (estimating) est_chunk(est, va); else scan_chunk(L, id, va, cbase + pair * 64, n_points);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");  // vb = chunk 2*pair + 1
+        if (pair == 0) {
+          tmem_ld32_nowait(tbase + 64u, va);
+        } else {
+          // the whole row slab is in registers: hand the accumulator buffer back, then start on the next tile
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(&tempty[b]);
+          if (c + 1 < n_visit) {
+            mbar_wait(&tfull[b ^ 1], (uint32_t)(((c + 1) >> 1) & 1));
+            tc_fence_after();
+            tmem_ld32_nowait(lane_base + (uint32_t)((b ^ 1) * (128 * QH)), va);
+          }
         }
-        scan_chunk(L, id, va, cbase + half * 64, n_points);
-        scan_chunk(L, id, vb, cbase + half * 64 + 32, n_points);
+        if (estimating) est_chunk(est, vb); else scan_chunk(L, id, vb, cbase + pair * 64 + 32, n_points);
       }
     }
     if (valid) {
@@ -400,64 +477,92 @@ knn_pass1_tc_kernel(const __half* __restrict__ Aimg, const __half* __restrict__ 
 
 }  // namespace
 
-// widest K axis the kernel can stage: one query image + NSTAGE quarter-slices of a candidate image in 227 KB
+// widest K axis the kernel can stage: one query image + three quarter-slices of a candidate image in 227 KB
 bool knn_tc_supported(int d) { return 3 * d + 3 <= 512; }
+
+bool knn_tc_shape(const sb2_ctx* ctx, int d, int terms, KnnTcShape* out) {
+  // 256 queries per CTA with whole candidate images per ring stage when that fits; otherwise 128 queries per CTA
+  // and the candidate K axis staged in 1, 2 or 4 slices.  The ring takes whatever shared memory is left (<= MAXST).
+  const size_t cap = ctx->prop.sharedMemPerBlockOptin;
+  const int cand[4][2] = {{2, 1}, {1, 1}, {1, 2}, {1, 4}};
+  for (int t = 0; t < 4; ++t) {
+    const int unit = 16 * cand[t][1];
+    const int kp = ((terms * d + 3 + unit - 1) / unit) * unit;
+    const size_t tb = (size_t)TM * kp * 2, part = tb / cand[t][1];
+    if (cand[t][0] * tb + 3 * part + BAR_BYTES > cap) continue;
+    int nst = (int)((cap - BAR_BYTES - cand[t][0] * tb) / part);
+    if (nst > MAXST) nst = MAXST;
+    out->qh = cand[t][0]; out->nsplit = cand[t][1]; out->nstage = nst; out->kpad = kp; out->terms = terms;
+    out->smem = cand[t][0] * tb + (size_t)nst * part + BAR_BYTES;
+    return true;
+  }
+  return false;
+}
+
+size_t knn_tc_image_halves(const KnnTcShape& sh, int64_t n_rows) {
+  const int64_t n_tiles = ceil_div64(n_rows, TM);
+  return (size_t)(n_tiles + (n_tiles & 1) + 2) * TM * sh.kpad;  // A images may be consumed in pairs
+}
+
+int32_t knn_tc_build_images(sb2_ctx* ctx, const KnnTcShape& sh, const float* d_x, int64_t n_rows, int d,
+                            const unsigned int* d_maxnorm_bits, const int32_t* d_gather, int64_t gather_base,
+                            __half* Aimg, __half* Bimg, float* d_inv_s2, float* d_dnorm, unsigned int* d_dmax_bits) {
+  const int64_t n_tiles = ceil_div64(n_rows, TM);
+  const int64_t n_tiles_alloc = n_tiles + (n_tiles & 1) + 2;
+  knn_tc_prep_kernel<<<(unsigned)n_tiles_alloc, 256, 0, ctx->stream>>>(d_x, n_rows, d, sh.kpad, sh.terms, d_maxnorm_bits, d_gather,
+                                                                        gather_base, Aimg, Bimg, d_inv_s2, d_dnorm, d_dmax_bits);
+  SB2_LAUNCH_CHECK(ctx);
+  return SB2_OK;
+}
 
 namespace {
 template <int NG, int QH>
-cudaError_t launch_tc(unsigned grid, size_t smem, cudaStream_t st, const __half* A, const __half* B, int kpad, int nsplit,
-                      int64_t n_tiles, int64_t qtile0, int64_t n_query, int32_t n_points, float* cs, int32_t* ci) {
-  cudaError_t e = cudaFuncSetAttribute(knn_pass1_tc_kernel<NG, QH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+cudaError_t launch_tc(unsigned grid, const KnnTcShape& sh, cudaStream_t st, const __half* A, const __half* B, int64_t n_tiles,
+                      int64_t n_est, int64_t est_stride, int64_t qtile0, int64_t n_query, int32_t n_points, float* cs,
+                      int32_t* ci) {
+  cudaError_t e = cudaFuncSetAttribute(knn_pass1_tc_kernel<NG, QH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sh.smem);
   if (e != cudaSuccess) return e;
-  knn_pass1_tc_kernel<NG, QH><<<grid, TC_THREADS, smem, st>>>(A, B, kpad, nsplit, n_tiles, qtile0, n_query, n_points, cs, ci);
+  knn_pass1_tc_kernel<NG, QH><<<grid, TC_THREADS, sh.smem, st>>>(A, B, sh.kpad, sh.nsplit, sh.nstage, n_tiles, n_est, est_stride, qtile0,
+                                                                 n_query, n_points, cs, ci);
   return cudaSuccess;
 }
 }  // namespace
 
-int32_t knn_tc_pass1(sb2_ctx* ctx, ScratchScope& scr, const float* d_x, int64_t n_points, int d,
-                     const unsigned int* d_maxnorm_bits, int64_t q0, int64_t n_query, int list_m, float* cand_score,
-                     int32_t* cand_idx, float* d_inv_s2, double* eps_coef, cudaEvent_t ev_after_prep,
-                     double* issued_flops) {
+int32_t knn_tc_sweep(sb2_ctx* ctx, const KnnTcShape& sh, const __half* Aimg, int64_t a_tile0, const __half* Bimg,
+                     int64_t n_points, int64_t n_query, int list_m, float* cand_score, int32_t* cand_idx, double* issued_flops) {
   cudaStream_t st = ctx->stream;
-  // tile shape: 256 queries per CTA with whole candidate images per stage when that fits (d <= 52); otherwise
-  // 128 queries per CTA and the candidate K axis staged in 1, 2 or 4 slices
-  const size_t smem_cap = ctx->prop.sharedMemPerBlockOptin;
-  int qh = 0, nsplit = 0, kpad = 0;
-  const int cand[4][2] = {{2, 1}, {1, 1}, {1, 2}, {1, 4}};
-  for (int t = 0; t < 4 && !qh; ++t) {
-    const int unit = 16 * cand[t][1];
-    const int kp = ((3 * d + 3 + unit - 1) / unit) * unit;
-    const size_t tb = (size_t)TM * kp * 2;
-    if (cand[t][0] * tb + NSTAGE * (tb / cand[t][1]) + 128 <= smem_cap) { qh = cand[t][0]; nsplit = cand[t][1]; kpad = kp; }
-  }
-  SB2_CHECK_ARG(qh != 0, "tensor-core kNN tile does not fit shared memory");
-  int64_t n_tiles = ceil_div64(n_points, TM);
-  const int64_t n_tiles_alloc = n_tiles + (n_tiles & 1) + 2;  // A images may be consumed in pairs
-  const size_t img_halves = (size_t)TM * kpad;
-  __half *Aimg, *Bimg;
-  SB2_TRY(scr.alloc(&Aimg, (size_t)n_tiles_alloc * img_halves));
-  SB2_TRY(scr.alloc(&Bimg, (size_t)n_tiles_alloc * img_halves));
-  knn_tc_prep_kernel<<<(unsigned)n_tiles_alloc, 256, 0, st>>>(d_x, n_points, d, kpad, d_maxnorm_bits, Aimg, Bimg, d_inv_s2);
-  SB2_LAUNCH_CHECK(ctx);
-  if (ev_after_prep) SB2_CUDA(cudaEventRecord(ev_after_prep, st));
-  const int64_t q_ctas = ceil_div64(n_query, (int64_t)qh * TM);
-  if (issued_flops) *issued_flops = 2.0 * (double)(q_ctas * qh * TM) * (double)(n_tiles * TM) * (double)kpad;
-  const uint32_t tile_b = (uint32_t)TM * kpad * 2;
-  const size_t smem = (size_t)qh * tile_b + (size_t)NSTAGE * (tile_b / nsplit) + 128;
+  const int64_t n_tiles = ceil_div64(n_points, TM);
+  const int64_t q_ctas = ceil_div64(n_query, (int64_t)sh.qh * TM);
+  // threshold estimate: EST_R chunk maxima over every est_stride-th tile put the starting tau at about rank
+  // EST_R * est_stride; aim at ~3 * list_m so that the list still fills (and ends at its usual rank) for nearly all rows
+  int64_t est_stride = (3 * list_m) / EST_R, n_est = n_tiles / est_stride;
+  const char* est_env = getenv("SB2_KNN_EST");
+  if (est_env) est_stride = atoi(est_env) > 0 ? atoi(est_env) : est_stride, n_est = atoi(est_env) > 0 ? n_tiles / est_stride : 0;
+  if (n_tiles < 64 * est_stride) n_est = 0;  // small problems: a cold start is cheap
+  if (issued_flops) *issued_flops += 2.0 * (double)(q_ctas * sh.qh * TM) * (double)((n_tiles + n_est) * TM) * (double)sh.kpad;
   SB2_CHECK_ARG(list_m == 32 || list_m == 64, "list_m must be 32 or 64");
   cudaError_t le;
   const unsigned grid = (unsigned)q_ctas;
-  const int64_t qt0 = q0 / TM;
   const int32_t np = (int32_t)n_points;
-  if (list_m == 32 && qh == 2) le = launch_tc<4, 2>(grid, smem, st, Aimg, Bimg, kpad, nsplit, n_tiles, qt0, n_query, np, cand_score, cand_idx);
-  else if (list_m == 32) le = launch_tc<4, 1>(grid, smem, st, Aimg, Bimg, kpad, nsplit, n_tiles, qt0, n_query, np, cand_score, cand_idx);
-  else if (qh == 2) le = launch_tc<8, 2>(grid, smem, st, Aimg, Bimg, kpad, nsplit, n_tiles, qt0, n_query, np, cand_score, cand_idx);
-  else le = launch_tc<8, 1>(grid, smem, st, Aimg, Bimg, kpad, nsplit, n_tiles, qt0, n_query, np, cand_score, cand_idx);
+  if (list_m == 32 && sh.qh == 2) le = launch_tc<4, 2>(grid, sh, st, Aimg, Bimg, n_tiles, n_est, est_stride, a_tile0, n_query, np, cand_score, cand_idx);
+  else if (list_m == 32) le = launch_tc<4, 1>(grid, sh, st, Aimg, Bimg, n_tiles, n_est, est_stride, a_tile0, n_query, np, cand_score, cand_idx);
+  else if (sh.qh == 2) le = launch_tc<8, 2>(grid, sh, st, Aimg, Bimg, n_tiles, n_est, est_stride, a_tile0, n_query, np, cand_score, cand_idx);
+  else le = launch_tc<8, 1>(grid, sh, st, Aimg, Bimg, n_tiles, n_est, est_stride, a_tile0, n_query, np, cand_score, cand_idx);
   SB2_CUDA(le);
   SB2_LAUNCH_CHECK(ctx);
-  // error of the split-precision score, relative to (R^2/2 + |q| R): operand split 3*2^-24 + dropped lo*lo 2^-24
-  // + fp16 three-way norm 2^-33 + fp32 accumulation in the tensor pipe: kpad/16 accumulator updates of one ulp
-  // each plus the alignment loss inside a 16-product group, bounded by 1.6 * kpad * 2^-24 of sum |a_i b_i|
-  *eps_coef = (1.6 * kpad + 8.0) * 5.9604644775390625e-08;
   return SB2_OK;
+}
+
+void knn_tc_error_coefs(const KnnTcShape& sh, double* c_q, double* c_n) {
+  // |s_computed - s_true| <= c_q |q| R + c_n R^2 / 2   (R = largest norm in the data set, everything after scaling)
+  //   fp32 accumulation in the tensor pipe: kpad/16 accumulator updates of one ulp each plus the alignment loss
+  //   inside a 16-product group, bounded by 1.6 * kpad * 2^-24 of sum |a_i b_i| <= |q| R + R^2 / 2;
+  //   three-way fp16 split of the norm: 2^-33 R^2/2; sub-normal halves: < 2^-27 R^2/2 since R >= 100 after scaling
+  //   terms = 3: operand split 3 * 2^-24 |q| R, dropped lo*lo term 2^-22 * 2^-2 |q| R
+  //   terms = 1: |q.c - q_hi.c_hi| <= |q - q_hi| |c| + |q_hi| |c - c_hi|: the re-score kernel adds this term from
+  //              the measured residual norms (dnorm / dmax of knn_tc_build_images), not from the 2^-11 worst case
+  const double u24 = 5.9604644775390625e-08;
+  const double acc = 1.6 * sh.kpad * u24;
+  *c_n = acc + 8.0 * u24;
+  *c_q = acc + (sh.terms == 3 ? 8.0 * u24 : 0.0);
 }

@@ -305,10 +305,8 @@ def neighbors(adata, n_neighbors: int = 15, n_pcs: int | None = None, *, distanc
         # built-in exact kNN: (idx, dist) stay in HBM between the search and the fuzzy-set kernels, so the
         # n x k lists cross PCIe once (device -> host) instead of three times
         xd = x.toarray() if sparse.issparse(x) else np.asarray(x)
-        knn_indices, knn_distances, conn = _ops.knn_and_connectivities(np.ascontiguousarray(xd, dtype=np.float32),
-                                                                        min(n_neighbors, adata.shape[0]))
-        if knn_indices.shape[1] > n_neighbors:
-            knn_indices, knn_distances = knn_indices[:, :n_neighbors], knn_distances[:, :n_neighbors]
+        dist_csr, conn = _ops.knn_and_connectivities(np.ascontiguousarray(xd, dtype=np.float32),
+                                                     min(n_neighbors, adata.shape[0]))
     else:
         if transformer is None or isinstance(transformer, str):
             transformer = B200KNNTransformer(n_neighbors=n_neighbors, metric=metric)
@@ -318,7 +316,7 @@ def neighbors(adata, n_neighbors: int = 15, n_pcs: int | None = None, *, distanc
             conn, _, _ = _ops.fuzzy_simplicial_set(knn_indices, knn_distances)
         else:  # 'gauss' | 'jaccard' (src/scanpy/neighbors/__init__.py:675-701)
             conn = _ops.knn_connectivities(knn_indices, knn_distances, method)
-    dist_csr = _get_sparse_matrix_from_indices_distances(knn_indices, knn_distances, keep_self=False)
+        dist_csr = _get_sparse_matrix_from_indices_distances(knn_indices, knn_distances, keep_self=False)
 
     if key_added is None:
         key_added, conns_key, dists_key = "neighbors", "connectivities", "distances"

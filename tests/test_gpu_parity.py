@@ -161,6 +161,30 @@ def test_knn_identical_index_sets(n, d, k):
     np.testing.assert_allclose(dist[:, 1:], od[:, 1:], rtol=1e-6, atol=1e-7)  # (sklearn's self distance is ~5e-7, not 0)
 
 
+def test_knn_threshold_estimate_and_tiers_agree_with_oracle(monkeypatch):
+    # large enough (>= 1024 candidate tiles) for the sampled starting threshold of the tensor sweep; every
+    # configuration of the tiers must return the same exact result, and that result must match the oracle
+    rs = np.random.RandomState(5)
+    n, d, k = 140_000, 12, 15
+    c = rs.standard_normal((20, d)).astype(np.float32) * 4
+    x = (c[rs.randint(0, 20, n)] + rs.standard_normal((n, d))).astype(np.float32)
+    idx, dist, info = _ops.knn(x, k)
+    assert info["pass1_tensor"] == 1
+    rows = rs.choice(n, 1500, replace=False)
+    from sklearn.neighbors import NearestNeighbors
+    nn = NearestNeighbors(n_neighbors=k, algorithm="brute").fit(x.astype(np.float64))
+    od, oi = nn.kneighbors(x[rows].astype(np.float64))
+    assert oknn.same_neighbor_sets(idx[rows], dist[rows], oi, od).all()
+    np.testing.assert_allclose(dist[rows][:, 1:], od[:, 1:], rtol=1e-6, atol=1e-7)
+    for env in (dict(SB2_KNN_EST="0"), dict(SB2_KNN_TIERS="3"), dict(SB2_KNN_TIERS="3", SB2_KNN_EST="0"), dict(SB2_KNN_LIST="64")):
+        for key in ("SB2_KNN_EST", "SB2_KNN_TIERS", "SB2_KNN_LIST"):
+            monkeypatch.delenv(key, raising=False)
+        for key, val in env.items():
+            monkeypatch.setenv(key, val)
+        idx2, dist2, _ = _ops.knn(x, k)
+        assert (idx2 == idx).all() and (dist2 == dist).all(), env
+
+
 def test_knn_duplicates_zero_rows_and_scale():
     rs = np.random.RandomState(3)
     x = np.zeros((600, 12), np.float32)          # 200 all-zero cells (legal: empty CSR rows) -> exact ties
