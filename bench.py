@@ -251,9 +251,14 @@ def run_b200(a, rank, world, local_rank):
                         peak_source=("MEASURED_PEAKS.json bf16_tflops_sustained (kernel timed inside a long step)" if peaks else "fallback 1.4 PFLOP/s sustained"),
                         launch_ms=ki["pass1_ms"], algorithmic_flops_per_launch=ki["pass1_flops"],
                         issued_tensor_tflops=issued, frac_issued=issued / peak_tensor,
-                        note=("achieved counts the ALGORITHMIC 2*n_q*n*d flops of the pairwise-distance sweep; the kernel issues "
-                              "3.2x that many fp16 tensor flops (hi/lo split operands on a concatenated K axis of 160 instead of 50, "
-                              "the price of an fp32-accurate score) - issued_tensor_tflops / frac_issued say how busy the tensor pipe is"),
+                        note=("achieved counts the ALGORITHMIC 2*n_q*n*d flops of the pairwise-distance sweep over the summed duration "
+                              "of its launches (pilot wave + rest; rows the fp16 tier cannot certify are swept again in split "
+                              "precision, n_resweep of them). The fp16 tier issues K = d+3 padded to 64 instead of 50, plus a 1/16 "
+                              "sample of the candidate tiles for the starting threshold: issued_tensor_tflops / frac_issued say how "
+                              "busy the tensor pipe is. Each 256x128 score tile is 8 MMAs (512 tensor cycles) against one TMEM "
+                              "hand-off + 4 tcgen05.ld round trips per epilogue warp, so the sweep is paced by the accumulator "
+                              "hand-off, not by the MMAs (DESIGN.md section 5)"),
+                        n_resweep=ki.get("n_resweep", 0),
                         share_of_step=ki["pass1_ms"] / ms_step)
     else:
         fp32_peak = 148 * 128 * 2 * sm_max * 1e6 / 1e12
@@ -265,7 +270,7 @@ def run_b200(a, rank, world, local_rank):
                 higher_is_better=True, scaling="strong", vs_baseline=None, dtype="f32", data="synthetic",
                 config=workload_config(a, world), e2e=e2e, gpu_launches=int(launches), clocks=clocks, roofline=roofline,
                 stages=dict(pca_iterations=out["pca"]["iterations"], pca_converged=out["pca"]["converged"],
-                            knn_uncertified_rows=ki["n_uncertified"], leiden=out["leiden_info"], n_communities=out["n_communities"],
+                            knn_uncertified_rows=ki["n_uncertified"], knn_resweep_rows=ki.get("n_resweep", 0), leiden=out["leiden_info"], n_communities=out["n_communities"],
                             modularity=out["modularity"]))
     if world == 1 and not a.no_cpu_baseline:
         line["cpu_baseline"] = cpu_reference_sample(a)

@@ -35,8 +35,8 @@ namespace {
 
 constexpr int TM = 128;           // rows per operand tile (UMMA M and N)
 constexpr int MAXST = 8;          // upper bound of the candidate ring depth (runtime nstage <= MAXST)
-constexpr int BAR_BYTES = 256;    // mbarriers + TMEM slot behind the ring
-constexpr int TC_THREADS = 320;   // 10 warps
+constexpr int BAR_BYTES = 1024;   // mbarriers + TMEM slot IN FRONT of the operand images (a fixed address: see the MMA warp)
+constexpr int TC_THREADS = 352;   // 11 warps: producer, MMA issuer (half 0), 8 epilogue warps, MMA issuer (half 1)
 constexpr uint32_t SBO = 128;     // bytes between 8-row groups (core matrices contiguous)
 constexpr uint32_t LBO = TM * 16; // bytes between K-chunks (8 fp16) : [kc][row-group][8][8]
 
@@ -86,7 +86,36 @@ __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr) {
 // instruction descriptor: D=F32, A=B=F16, both K-major, N=128, M=128 (cute::UMMA::InstrDescriptor bit layout)
 constexpr uint32_t IDESC = (1u << 4) | (0u << 7) | (0u << 10) | (0u << 15) | (0u << 16) | ((128u >> 3) << 17) | ((128u >> 4) << 24);
 
-__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t accumulate) {
+// MMA issue.  The whole warp runs the (warp-uniform) issue loop and the single issuing thread is chosen INSIDE the
+// asm block (elect.sync): ptxas then keeps descriptors, TMEM addresses and loop counters on the uniform datapath
+// and emits back-to-back UTCHMMA.  (Issuing from an `if (lane == 0)` branch makes every operand "divergent": each
+// MMA is then wrapped in an ELECT / R2UR.BROADCAST waterfall of ~20 dependent instructions, ~130 cycles per MMA -
+// twice the 64 cycles the tensor pipe needs for it.)  Descriptors are (lo, hi) halves: only lo moves along K.
+template <bool ACC>
+__device__ __forceinline__ void umma_f16_elect(uint32_t tmem_d, uint32_t da_lo, uint32_t db_lo, uint32_t desc_hi) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p, pe;\n"
+      ".reg .b64 da, db;\n"
+      "setp.ne.b32 p, %5, 0;\n"
+      "mov.b64 da, {%1, %3};\n"
+      "mov.b64 db, {%2, %3};\n"
+      "elect.sync _|pe, 0xffffffff;\n"
+      "@pe tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %4, p;\n"
+      "}\n" ::"r"(tmem_d),
+      "r"(da_lo), "r"(db_lo), "r"(desc_hi), "r"(IDESC), "n"(ACC ? 1 : 0)
+      : "memory");
+}
+__device__ __forceinline__ void tc_commit_elect(uint64_t* bar) {
+  asm volatile(
+      "{\n"
+      ".reg .pred pe;\n"
+      "elect.sync _|pe, 0xffffffff;\n"
+      "@pe tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n"
+      "}\n" ::"r"(smem_u32(bar))
+      : "memory");
+}
+[[maybe_unused]] __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t accumulate) {
   asm volatile(
       "{\n"
       ".reg .pred p;\n"
@@ -309,31 +338,41 @@ __device__ __forceinline__ void tmem_ld32_nowait(uint32_t taddr, uint32_t (&v)[3
 
 // QH = query halves per CTA (2: 256 queries, 1: 128 queries); nsplit = pieces the K axis of a candidate image is
 // staged in (1 when a whole image fits a ring stage; 2 or 4 for wide embeddings, d up to 150).
-template <int NG, int QH>
+// SB2_KNN_DBG=1: cycle stamps of CTA 0's hand-offs (visits [DBG_C0, DBG_C0 + DBG_N)) for pipeline analysis
+__device__ long long g_knn_dbg[8 * 64];
+__device__ long long g_knn_dbg2[3 * 8 * 16];  // [tfull seen | release | done][epilogue warp][visit - DBG_C0]
+__device__ int g_knn_dbg_mode;  // DBG build only: 1 = epilogue skips the scans, 2 = epilogue also skips the TMEM loads
+constexpr int DBG_C0 = 200, DBG_N = 64;
+template <int NG, int QH, bool DBG = false>
 __global__ void __launch_bounds__(TC_THREADS, 1)
-knn_pass1_tc_kernel(const __half* __restrict__ Aimg, const __half* __restrict__ Bimg, int kpad, int nsplit, int nstage, int64_t n_btiles,
+knn_pass1_tc_kernel(const __half* __restrict__ Aimg, const __half* __restrict__ Bimg, int nks, int nsplit, int nstage, uint32_t mma_part16,
+                    uint32_t mma_tile16, int mma_visits, int64_t n_btiles,
                     int64_t n_est, int64_t est_stride,
                     int64_t qtile0, int64_t n_query, int32_t n_points, float* __restrict__ cand_score,
                     int32_t* __restrict__ cand_idx) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
-  const uint32_t tile_b = (uint32_t)TM * (uint32_t)kpad * 2u;  // bytes per 128-row image
-  const uint32_t part_b = tile_b / (uint32_t)nsplit;  // bytes per staged K-slice of a candidate image
-  unsigned char* As = smem_raw;                     // QH images (128*QH queries)
-  unsigned char* Bs0 = smem_raw + QH * tile_b;      // nstage slices
-  uint64_t* bars = reinterpret_cast<uint64_t*>(Bs0 + (size_t)nstage * part_b);
+  // nks = k-steps (16 columns of the K axis) per staged slice.  Everything the MMA warp derives its operands from is
+  // a kernel parameter combined by add / multiply only: a division here would move the values to the vector
+  // datapath and every tcgen05.mma would need its operands copied back (R2UR) - see umma_f16_elect.
+  const uint32_t part_b = (uint32_t)(TM * 16 * 2) * (uint32_t)nks;  // bytes per staged K-slice of a candidate image
+  const uint32_t tile_b = part_b * (uint32_t)nsplit;                // bytes per 128-row image
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw);   // fixed offset: barrier addresses stay uniform values
+  unsigned char* As = smem_raw + BAR_BYTES;                 // QH images (128*QH queries)
+  unsigned char* Bs0 = As + QH * tile_b;                    // nstage slices
   uint64_t* full = bars;                  // [MAXST] producer -> MMA
   uint64_t* empty = bars + MAXST;         // [MAXST] MMA (commit) -> producer
   uint64_t* afull = bars + 2 * MAXST;     // [1]
-  uint64_t* tfull = bars + 2 * MAXST + 1;    // [2] MMA (commit) -> epilogue
-  uint64_t* tempty = bars + 2 * MAXST + 3;   // [2] epilogue -> MMA
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * MAXST + 5);
-  static_assert((2 * MAXST + 5) * 8 + 4 <= BAR_BYTES, "barrier block");
+  uint64_t* tfull = bars + 2 * MAXST + 1;    // [2 buffers][2 halves] MMA (commit) -> epilogue warps of that half
+  uint64_t* tempty = bars + 2 * MAXST + 5;   // [2 buffers][2 halves] epilogue warps of that half -> its MMA issuer
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * MAXST + 17);
+  static_assert((2 * MAXST + 17) * 8 + 4 <= BAR_BYTES, "barrier block");
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // warp index through a shuffle: tells the compiler it is warp-uniform, so each role's branch is a converged region
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
-    for (int s = 0; s < nstage; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    for (int s = 0; s < nstage; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], QH); }
     mbar_init(afull, 1);
-    for (int b = 0; b < 2; ++b) { mbar_init(&tfull[b], 1); mbar_init(&tempty[b], 4 * QH); }
+    for (int b = 0; b < 4; ++b) { mbar_init(&tfull[b], 1); mbar_init(&tempty[b], 4); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -344,7 +383,7 @@ knn_pass1_tc_kernel(const __half* __restrict__ Aimg, const __half* __restrict__ 
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  const int nks = kpad / 16 / nsplit;  // k-steps per staged slice
+  if (tmem_base != 0) __trap();  // a 512-column allocation can only start at lane 0, column 0 (the MMA warp relies on it)
 
   if (warp == 0) {
     // ---------------- producer ----------------
@@ -354,49 +393,82 @@ knn_pass1_tc_kernel(const __half* __restrict__ Aimg, const __half* __restrict__ 
         bulk_g2s(As + (size_t)h * tile_b,
                  reinterpret_cast<const unsigned char*>(Aimg) + (size_t)(qtile0 + QH * (int64_t)blockIdx.x + h) * tile_b, tile_b, afull);
       // visit order: n_est sample tiles (every est_stride-th) for the threshold estimate, then every tile
-      int64_t it = 0;
+      int s = 0;
+      uint32_t use_phase = 1;  // parity of the previous use of stage s (first lap: nothing to wait for)
+      bool first_lap = true;
       for (int64_t v = 0; v < n_est + n_btiles; ++v) {
         const int64_t c = v < n_est ? v * est_stride : v - n_est;
-        for (int p = 0; p < nsplit; ++p, ++it) {
-          const int s = (int)(it % nstage);
-          const int64_t use = it / nstage;
-          if (use > 0) mbar_wait(&empty[s], (uint32_t)((use - 1) & 1));
+        for (int p = 0; p < nsplit; ++p) {
+          if (!first_lap) mbar_wait(&empty[s], use_phase);
           mbar_expect_tx(&full[s], part_b);
           bulk_g2s(Bs0 + (size_t)s * part_b, reinterpret_cast<const unsigned char*>(Bimg) + (size_t)c * tile_b + (size_t)p * part_b,
                    part_b, &full[s]);
+          if (++s == nstage) { s = 0; use_phase ^= 1u; first_lap = false; }
         }
       }
     }
-  } else if (warp == 1) {
-    // ---------------- MMA issuer (one thread) ----------------
-    if (lane == 0) {
+  } else if (warp == 1 || (warp == 10 && QH == 2)) {
+    // ---------------- MMA issuers (whole warp, elected thread issues) ----------------
+    // One issuer per query half, on different SM sub-partitions (warp 1 -> SMSP 1, warp 10 -> SMSP 2), each with
+    // its own accumulator hand-off (tfull / tempty[2*buffer + half], one waiter per barrier): the epilogue warps of
+    // half 0 start on their slab while the MMAs of half 1 are still running.  (Measured: a tcgen05.mma that finds
+    // the tensor queue full stalls its sub-partition's dispatch, so the two epilogue warps living next to an issuer
+    // fall behind the others; rotating whole visits over three issuer warps was tried and is not faster.)
+    {
+      const int h = warp == 1 ? 0 : 1;
       mbar_wait(afull, 0);
-      const uint32_t a_addr = smem_u32(As);
-      int64_t it = 0;
-      for (int64_t c = 0; c < n_est + n_btiles; ++c) {  // c counts visits here (the operands come through the ring)
-        const int b = (int)(c & 1);
-        const int64_t useb = c >> 1;
-        for (int p = 0; p < nsplit; ++p, ++it) {
-          const int s = (int)(it % nstage);
-          mbar_wait(&full[s], (uint32_t)((it / nstage) & 1));
-          if (p == 0 && useb > 0) mbar_wait(&tempty[b], (uint32_t)((useb - 1) & 1));
+      // descriptor halves: lo = start address >> 4 | LBO field (bits 16..29); hi = SBO field | version; one k-step
+      // (two 8-column K-chunks) advances the start address by 2*LBO bytes
+      const uint64_t d0 = umma_desc(0);
+      const uint32_t desc_hi = (uint32_t)(d0 >> 32);
+      const uint32_t a_lo0 = (uint32_t)d0 | (((smem_u32(smem_raw) + BAR_BYTES) & 0x3FFFFu) >> 4);  // As
+      const uint32_t b_lo0 = a_lo0 + (uint32_t)QH * mma_tile16;                       // Bs0 = As + QH images
+      constexpr uint32_t KSTEP16 = (2u * LBO) >> 4;
+      int s = 0;
+      uint32_t ring_phase = 0;
+      // mma_part16 / mma_tile16 / mma_visits repeat part_b >> 4, tile_b >> 4 and n_est + n_btiles as parameters of
+      // their own, so that this warp's copies stay on the uniform datapath (the other warps use the vector ones)
+      for (int c = 0; c < mma_visits; ++c) {  // c counts visits here (the operands come through the ring)
+        const int b = c & 1;
+        const int useb = c >> 1;
+        for (int p = 0; p < nsplit; ++p) {
+          const bool dbg = DBG && blockIdx.x == 0 && warp == 1 && lane == 0 && c >= DBG_C0 && c < DBG_C0 + DBG_N;
+          if (dbg) g_knn_dbg[0 * 64 + (c - DBG_C0)] = clock64();
+          mbar_wait(&full[s], ring_phase);
+          if (dbg) g_knn_dbg[1 * 64 + (c - DBG_C0)] = clock64();
+          if (p == 0 && useb > 0) mbar_wait(&tempty[2 * b + h], (uint32_t)((useb - 1) & 1));
+          if (dbg) g_knn_dbg[2 * 64 + (c - DBG_C0)] = clock64();
           tc_fence_after();
-          const uint32_t b_addr = smem_u32(Bs0 + (size_t)s * part_b);
-#pragma unroll
-          for (int h = 0; h < QH; ++h) {
-            const uint32_t tm = tmem_base + (uint32_t)(b * (128 * QH) + h * 128);
-            for (int j = 0; j < nks; ++j) {
-              const uint64_t da = umma_desc(a_addr + (uint32_t)h * tile_b + (uint32_t)(p * nks + j) * 2u * LBO);
-              const uint64_t db = umma_desc(b_addr + (uint32_t)j * 2u * LBO);
-              umma_f16(tm, da, db, (p > 0 || j > 0) ? 1u : 0u);
-            }
+          // the CTA owns all 512 TMEM columns, so its allocation starts at column 0 (checked after the alloc)
+          const uint32_t tm = (uint32_t)(b * (128 * QH) + h * 128);
+          uint32_t da = a_lo0 + (uint32_t)h * mma_tile16 + (uint32_t)(p * nks) * KSTEP16;
+          uint32_t db = b_lo0 + (uint32_t)s * mma_part16;
+          if (p == 0) umma_f16_elect<false>(tm, da, db, desc_hi); else umma_f16_elect<true>(tm, da, db, desc_hi);
+#pragma unroll 4
+          for (int j = 1; j < nks; ++j) {
+            da += KSTEP16;
+            db += KSTEP16;
+            umma_f16_elect<true>(tm, da, db, desc_hi);
           }
-          tc_commit(&empty[s]);   // smem stage reusable once these MMAs have read it
+          tc_commit_elect(&empty[s]);   // smem stage reusable once the MMAs of both halves have read it (count QH)
+          if (++s == nstage) { s = 0; ring_phase ^= 1u; }
         }
-        tc_commit(&tfull[b]);     // accumulators of buffer b complete
+        tc_commit_elect(&tfull[2 * b + h]);  // accumulators of (buffer b, half h) complete
+        if (DBG && blockIdx.x == 0 && warp == 1 && lane == 0 && c >= DBG_C0 && c < DBG_C0 + DBG_N) g_knn_dbg[3 * 64 + (c - DBG_C0)] = clock64();
+      }
+      // teardown: the epilogue's release of the last visit means every TMEM read of this CTA has completed
+      if (warp == 1) {
+        if (mma_visits > 0) {
+          const int bl = (mma_visits - 1) & 1;
+          const uint32_t pl = (uint32_t)(((mma_visits - 1) >> 1) & 1);
+          mbar_wait(&tempty[2 * bl], pl);
+          if (QH == 2) mbar_wait(&tempty[2 * bl + 1], pl);
+        }
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(0u), "r"(512u) : "memory");
       }
     }
-  } else if (((warp - 2) >> 2) < QH) {
+  } else if (warp >= 2 && warp < 10 && ((warp - 2) >> 2) < QH) {
     // ---------------- epilogue: thread <-> query row ----------------
     const int e = warp - 2;                 // 0..7
     const int h = e >> 2;                   // query half
@@ -420,18 +492,23 @@ knn_pass1_tc_kernel(const __half* __restrict__ Aimg, const __half* __restrict__ 
     float est[EST_R];
 #pragma unroll
     for (int i = 0; i < EST_R; ++i) est[i] = -INFINITY;
-    // software pipeline over the 32-column chunks of the accumulator slabs: the tcgen05.ld of chunk g+1 is in
-    // flight while chunk g is examined (two register buffers, va: even chunks, vb: odd chunks)
+    // software pipeline over the 32-column chunks of the accumulator slabs, two register buffers (va, vb), two
+    // tcgen05.ld in flight: a slab costs two load round trips, and it is handed back to the MMA warp after the
+    // second one - before its last two chunks are examined.
     uint32_t va[32], vb[32];
     const uint32_t lane_base = tmem_base + ((uint32_t)(lgrp * 32) << 16) + (uint32_t)(h * 128);
-    mbar_wait(&tfull[0], 0);
+    mbar_wait(&tfull[h], 0);
     tc_fence_after();
     tmem_ld32_nowait(lane_base, va);
+    tmem_ld32_nowait(lane_base + 32u, vb);
     const int64_t n_visit = n_est + n_btiles;
+    const int dbg_mode = DBG ? g_knn_dbg_mode : 0;
     for (int64_t c = 0; c < n_visit; ++c) {
       const int b = (int)(c & 1);
       const uint32_t tbase = lane_base + (uint32_t)(b * (128 * QH));
+      const uint32_t nbase = lane_base + (uint32_t)((b ^ 1) * (128 * QH));
       const bool estimating = c < n_est;
+      const bool more = c + 1 < n_visit;
       const int32_t cbase = (int32_t)((estimating ? 0 : c - n_est) * TM);
       if (c == n_est) {
         const float t0 = valid ? est[EST_R - 1] : INFINITY;  // rows past n_query never accept anything
@@ -442,25 +519,36 @@ knn_pass1_tc_kernel(const __half* __restrict__ Aimg, const __half* __restrict__ 
         L.tau = t0;
       }
 #pragma unroll 1
-      for (int pair = 0; pair < 2; ++pair) {
-        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");  // va = chunk 2*pair
-        tmem_ld32_nowait(tbase + (uint32_t)(pair * 64 + 32), vb);
-        if (estimating) est_chunk(est, va); else scan_chunk(L, id, va, cbase + pair * 64, n_points);
-        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");  // vb = chunk 2*pair + 1
-        if (pair == 0) {
-          tmem_ld32_nowait(tbase + 64u, va);
-        } else {
-          // the whole row slab is in registers: hand the accumulator buffer back, then start on the next tile
+      for (int half = 0; half < 2; ++half) {
+        const bool dbg = DBG && blockIdx.x == 0 && warp == 2 && lane == 0 && c >= DBG_C0 && c < DBG_C0 + DBG_N;
+        if (dbg && half == 0) g_knn_dbg[4 * 64 + (c - DBG_C0)] = clock64();
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");  // va = chunk 2*half, vb = chunk 2*half + 1
+        if (half == 1) {
+          // the whole row slab is in registers: hand the accumulator buffer back
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive(&tempty[b]);
-          if (c + 1 < n_visit) {
-            mbar_wait(&tfull[b ^ 1], (uint32_t)(((c + 1) >> 1) & 1));
-            tc_fence_after();
-            tmem_ld32_nowait(lane_base + (uint32_t)((b ^ 1) * (128 * QH)), va);
-          }
+          if (lane == 0) mbar_arrive(&tempty[2 * b + h]);
+          if (dbg) g_knn_dbg[5 * 64 + (c - DBG_C0)] = clock64();
+          if (DBG && blockIdx.x == 0 && lane == 0 && c >= DBG_C0 && c < DBG_C0 + 16) g_knn_dbg2[(1 * 8 + e) * 16 + (c - DBG_C0)] = clock64();
         }
-        if (estimating) est_chunk(est, vb); else scan_chunk(L, id, vb, cbase + pair * 64 + 32, n_points);
+        if (dbg_mode == 0) { if (estimating) est_chunk(est, va); else scan_chunk(L, id, va, cbase + half * 64, n_points); }
+        if (half == 0) {
+          if (dbg_mode < 2) tmem_ld32_nowait(tbase + 64u, va);
+        } else if (more) {
+          mbar_wait(&tfull[2 * (b ^ 1) + h], (uint32_t)(((c + 1) >> 1) & 1));
+          if (dbg) g_knn_dbg[6 * 64 + (c - DBG_C0)] = clock64();  // tfull of visit c+1 seen
+          if (DBG && blockIdx.x == 0 && lane == 0 && c + 1 >= DBG_C0 && c + 1 < DBG_C0 + 16) g_knn_dbg2[(0 * 8 + e) * 16 + (c + 1 - DBG_C0)] = clock64();
+          tc_fence_after();
+          if (dbg_mode < 2) tmem_ld32_nowait(nbase, va);
+        }
+        if (dbg_mode == 0) { if (estimating) est_chunk(est, vb); else scan_chunk(L, id, vb, cbase + half * 64 + 32, n_points); }
+        if (half == 0) {
+          if (dbg_mode < 2) tmem_ld32_nowait(tbase + 96u, vb);
+        } else if (more) {
+          if (dbg_mode < 2) tmem_ld32_nowait(nbase + 32u, vb);
+        }
+        if (dbg && half == 1) g_knn_dbg[7 * 64 + (c - DBG_C0)] = clock64();  // visit c fully examined
+        if (DBG && half == 1 && blockIdx.x == 0 && lane == 0 && c >= DBG_C0 && c < DBG_C0 + 16) g_knn_dbg2[(2 * 8 + e) * 16 + (c - DBG_C0)] = clock64();
       }
     }
     if (valid) {
@@ -468,11 +556,8 @@ knn_pass1_tc_kernel(const __half* __restrict__ Aimg, const __half* __restrict__ 
       for (int i = 0; i < LM; ++i) sc[i] = L.ls[i];
     }
   }
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 1) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
-  }
+  // no CTA-wide barrier down here: code after the role branches would make ptxas treat the MMA warp's region as
+  // divergent (its operands then leave the uniform datapath, ~2x slower issue).  The MMA warp tears down by itself.
 }
 
 }  // namespace
@@ -522,7 +607,8 @@ cudaError_t launch_tc(unsigned grid, const KnnTcShape& sh, cudaStream_t st, cons
                       int32_t* ci) {
   cudaError_t e = cudaFuncSetAttribute(knn_pass1_tc_kernel<NG, QH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sh.smem);
   if (e != cudaSuccess) return e;
-  knn_pass1_tc_kernel<NG, QH><<<grid, TC_THREADS, sh.smem, st>>>(A, B, sh.kpad, sh.nsplit, sh.nstage, n_tiles, n_est, est_stride, qtile0,
+  knn_pass1_tc_kernel<NG, QH><<<grid, TC_THREADS, sh.smem, st>>>(A, B, sh.kpad / 16 / sh.nsplit, sh.nsplit, sh.nstage, (uint32_t)(TM * sh.kpad * 2 / sh.nsplit) >> 4,
+                                                                 (uint32_t)(TM * sh.kpad * 2) >> 4, (int)(n_tiles + n_est), n_tiles, n_est, est_stride, qtile0,
                                                                  n_query, n_points, cs, ci);
   return cudaSuccess;
 }
@@ -544,7 +630,41 @@ int32_t knn_tc_sweep(sb2_ctx* ctx, const KnnTcShape& sh, const __half* Aimg, int
   cudaError_t le;
   const unsigned grid = (unsigned)q_ctas;
   const int32_t np = (int32_t)n_points;
-  if (list_m == 32 && sh.qh == 2) le = launch_tc<4, 2>(grid, sh, st, Aimg, Bimg, n_tiles, n_est, est_stride, a_tile0, n_query, np, cand_score, cand_idx);
+  const char* dbg_env = getenv("SB2_KNN_DBG");
+  if (dbg_env && list_m == 32 && sh.qh == 2) {
+    const int mode = atoi(dbg_env) - 1;  // SB2_KNN_DBG=1: stamps only; 2: no scans; 3: no TMEM loads either
+    SB2_CUDA(cudaMemcpyToSymbol(g_knn_dbg_mode, &mode, sizeof(int)));
+    cudaEvent_t d0, d1;
+    cudaEventCreate(&d0); cudaEventCreate(&d1);
+    cudaEventRecord(d0, st);
+    le = cudaFuncSetAttribute(knn_pass1_tc_kernel<4, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sh.smem);
+    knn_pass1_tc_kernel<4, 2, true><<<grid, TC_THREADS, sh.smem, st>>>(Aimg, Bimg, sh.kpad / 16 / sh.nsplit, sh.nsplit, sh.nstage, (uint32_t)(TM * sh.kpad * 2 / sh.nsplit) >> 4,
+                                                                      (uint32_t)(TM * sh.kpad * 2) >> 4, (int)(n_tiles + n_est), n_tiles, n_est, est_stride,
+                                                                      a_tile0, n_query, np, cand_score, cand_idx);
+    long long h[8 * 64];
+    cudaEventRecord(d1, st);
+    SB2_CUDA(cudaStreamSynchronize(st));
+    float dms = 0;
+    cudaEventElapsedTime(&dms, d0, d1);
+    fprintf(stderr, "[dbg mode %d] kernel %.3f ms, grid %u, visits %lld\n", mode, dms, grid, (long long)(n_tiles + n_est));
+    SB2_CUDA(cudaMemcpyFromSymbol(h, g_knn_dbg, sizeof(h)));
+    fprintf(stderr, "visit  mma:wait_full  wait_tempty  issue   | epi: tfull_seen->consume  release  next_tfull_seen  done   (cycles, relative to visit's mma start)\n");
+    long long h2[3 * 8 * 16];
+    SB2_CUDA(cudaMemcpyFromSymbol(h2, g_knn_dbg2, sizeof(h2)));
+    for (int i = 4; i < 8; ++i) {
+      const long long t0 = h[0 * 64 + i];
+      fprintf(stderr, "visit %d (mma start %lld, issued +%lld): per epilogue warp  tfull_seen / release / done  rel. to mma start\n", DBG_C0 + i,
+              t0 - h[0 * 64 + 2], h[3 * 64 + i] - t0);
+      for (int w = 0; w < 8; ++w)
+        fprintf(stderr, "   warp %d: %6lld %6lld %6lld\n", w + 2, h2[(0 * 8 + w) * 16 + i] - t0, h2[(1 * 8 + w) * 16 + i] - t0, h2[(2 * 8 + w) * 16 + i] - t0);
+    }
+    for (int i = 2; i < 6; ++i) {
+      const long long t0 = h[0 * 64 + i];
+      fprintf(stderr, "%4d  start=%8lld  full+%5lld tempty+%5lld issued+%5lld | consume+%6lld release+%6lld nexttfull+%6lld done+%6lld\n", DBG_C0 + i,
+              t0 - h[0 * 64 + 2], h[1 * 64 + i] - t0, h[2 * 64 + i] - t0, h[3 * 64 + i] - t0, h[4 * 64 + i] - t0, h[5 * 64 + i] - t0,
+              h[6 * 64 + i] - t0, h[7 * 64 + i] - t0);
+    }
+  } else if (list_m == 32 && sh.qh == 2) le = launch_tc<4, 2>(grid, sh, st, Aimg, Bimg, n_tiles, n_est, est_stride, a_tile0, n_query, np, cand_score, cand_idx);
   else if (list_m == 32) le = launch_tc<4, 1>(grid, sh, st, Aimg, Bimg, n_tiles, n_est, est_stride, a_tile0, n_query, np, cand_score, cand_idx);
   else if (sh.qh == 2) le = launch_tc<8, 2>(grid, sh, st, Aimg, Bimg, n_tiles, n_est, est_stride, a_tile0, n_query, np, cand_score, cand_idx);
   else le = launch_tc<8, 1>(grid, sh, st, Aimg, Bimg, n_tiles, n_est, est_stride, a_tile0, n_query, np, cand_score, cand_idx);
