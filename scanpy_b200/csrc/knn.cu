@@ -335,6 +335,17 @@ __global__ void knn_rescore_kernel(const float* __restrict__ X, int64_t n_points
   }
 }
 
+// a handful of open rows is cheaper to scan exactly than to sweep again: move queue 1 behind queue 2
+__global__ void knn_append_queue_kernel(const int32_t* __restrict__ q_src, const double* __restrict__ ub_src, int64_t n,
+                                        int32_t* __restrict__ q_dst, double* __restrict__ ub_dst,
+                                        unsigned long long* __restrict__ cnt_dst) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const unsigned long long w = atomicAdd(cnt_dst, 1ull);
+  q_dst[w] = q_src[i];
+  ub_dst[w] = ub_src[i];
+}
+
 // exact fallback: one CTA per uncertified query, fp64 distances to every point
 constexpr int FB_THREADS = 256;
 constexpr int FB_BUF = 2048;
@@ -602,7 +613,15 @@ extern "C" int32_t sb2_knn_l2_f32(sb2_ctx* ctx, int64_t n_points, int32_t d, con
     if (!split_only) {
       // tier 2: gather the rows tier 1 left open and sweep them in split precision
       SB2_TRY(read_count(ctx, wcnt, &n_resweep));
-      if (n_resweep > 0) {
+      // a re-sweep occupies one CTA per 128..256 open rows for a whole pass over the candidates (~8 ms at 1.3M
+      // points however few rows there are); the exact scan streams the whole data set once per ROW (~45 us each at
+      // 1.3M x 50 once HBM saturates), so it only wins for a handful of rows
+      int64_t scan_slots = 16;
+      if (const char* se = getenv("SB2_KNN_SCAN_SLOTS")) scan_slots = atoll(se);  // 0 forces the re-sweep (tests)
+      if (n_resweep > 0 && n_resweep <= scan_slots) {
+        knn_append_queue_kernel<<<(unsigned)ceil_div64(n_resweep, 256), 256, 0, st>>>(wq1, wub1, n_resweep, wq2, wub2, wcnt + 1);
+        SB2_LAUNCH_CHECK(ctx);
+      } else if (n_resweep > 0) {
         if (!B3) {
           SB2_TRY(scr.alloc(&B3, knn_tc_image_halves(sh3, n_points)));
           SB2_TRY(knn_tc_build_images(ctx, sh3, d_x, n_points, d, maxnorm, nullptr, 0, nullptr, B3, inv_s2));
@@ -611,7 +630,8 @@ extern "C" int32_t sb2_knn_l2_f32(sb2_ctx* ctx, int64_t n_points, int32_t d, con
         SB2_TRY(scr.alloc(&Ag, knn_tc_image_halves(sh3, n_resweep)));
         SB2_TRY(knn_tc_build_images(ctx, sh3, d_x, n_resweep, d, maxnorm, wq1, q0, Ag, nullptr, inv_s2));
         SB2_TRY(evs.begin());
-        SB2_TRY(knn_tc_sweep(ctx, sh3, Ag, 0, B3, n_points, n_resweep, list_m, cand_score, cand_idx, &issued_flops));
+        // cold start: rows whose sampled threshold was too tight (fewer than k candidates beat it) must not fail twice
+        SB2_TRY(knn_tc_sweep(ctx, sh3, Ag, 0, B3, n_points, n_resweep, list_m, cand_score, cand_idx, &issued_flops, false));
         SB2_TRY(evs.end());
         SB2_TRY(launch_rescore(ctx, list_m, d_x, n_points, d, q0, 0, wq1, n_resweep, k, cand_score, cand_idx, maxnorm, inv_s2, cq3,
                                cn3, nullptr, nullptr, d_idx, d_dist, wq2, wub2, wcnt + 1));

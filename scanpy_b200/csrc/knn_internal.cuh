@@ -23,7 +23,9 @@ int32_t knn_tc_build_images(sb2_ctx* ctx, const KnnTcShape& sh, const float* d_x
                             __half* Aimg, __half* Bimg, float* d_inv_s2, float* d_dnorm = nullptr,
                             unsigned int* d_dmax_bits = nullptr);
 // proposals (unsorted, list_m per query; unused slots: score -inf, id -1) for the n_query rows whose A images
-// start at tile a_tile0; *issued_flops is incremented
+// start at tile a_tile0; *issued_flops is incremented; estimate = false starts the lists cold (no sampled threshold:
+// every row ends with its true top list_m, the certificate can only fail on exact ties)
 int32_t knn_tc_sweep(sb2_ctx* ctx, const KnnTcShape& sh, const __half* Aimg, int64_t a_tile0, const __half* Bimg,
-                     int64_t n_points, int64_t n_query, int list_m, float* cand_score, int32_t* cand_idx, double* issued_flops);
+                     int64_t n_points, int64_t n_query, int list_m, float* cand_score, int32_t* cand_idx, double* issued_flops,
+                     bool estimate = true);
 void knn_tc_error_coefs(const KnnTcShape& sh, double* c_q, double* c_n);

@@ -615,7 +615,8 @@ cudaError_t launch_tc(unsigned grid, const KnnTcShape& sh, cudaStream_t st, cons
 }  // namespace
 
 int32_t knn_tc_sweep(sb2_ctx* ctx, const KnnTcShape& sh, const __half* Aimg, int64_t a_tile0, const __half* Bimg,
-                     int64_t n_points, int64_t n_query, int list_m, float* cand_score, int32_t* cand_idx, double* issued_flops) {
+                     int64_t n_points, int64_t n_query, int list_m, float* cand_score, int32_t* cand_idx, double* issued_flops,
+                     bool estimate) {
   cudaStream_t st = ctx->stream;
   const int64_t n_tiles = ceil_div64(n_points, TM);
   const int64_t q_ctas = ceil_div64(n_query, (int64_t)sh.qh * TM);
@@ -624,7 +625,7 @@ int32_t knn_tc_sweep(sb2_ctx* ctx, const KnnTcShape& sh, const __half* Aimg, int
   int64_t est_stride = (3 * list_m) / EST_R, n_est = n_tiles / est_stride;
   const char* est_env = getenv("SB2_KNN_EST");
   if (est_env) est_stride = atoi(est_env) > 0 ? atoi(est_env) : est_stride, n_est = atoi(est_env) > 0 ? n_tiles / est_stride : 0;
-  if (n_tiles < 64 * est_stride) n_est = 0;  // small problems: a cold start is cheap
+  if (n_tiles < 64 * est_stride || !estimate) n_est = 0;  // small problems / re-sweeps: cold start
   if (issued_flops) *issued_flops += 2.0 * (double)(q_ctas * sh.qh * TM) * (double)((n_tiles + n_est) * TM) * (double)sh.kpad;
   SB2_CHECK_ARG(list_m == 32 || list_m == 64, "list_m must be 32 or 64");
   cudaError_t le;

@@ -176,13 +176,27 @@ def test_knn_threshold_estimate_and_tiers_agree_with_oracle(monkeypatch):
     od, oi = nn.kneighbors(x[rows].astype(np.float64))
     assert oknn.same_neighbor_sets(idx[rows], dist[rows], oi, od).all()
     np.testing.assert_allclose(dist[rows][:, 1:], od[:, 1:], rtol=1e-6, atol=1e-7)
-    for env in (dict(SB2_KNN_EST="0"), dict(SB2_KNN_TIERS="3"), dict(SB2_KNN_TIERS="3", SB2_KNN_EST="0"), dict(SB2_KNN_LIST="64")):
-        for key in ("SB2_KNN_EST", "SB2_KNN_TIERS", "SB2_KNN_LIST"):
+    for env in (dict(SB2_KNN_EST="0"), dict(SB2_KNN_TIERS="3"), dict(SB2_KNN_TIERS="3", SB2_KNN_EST="0"), dict(SB2_KNN_LIST="64"),
+                dict(SB2_KNN_SCAN_SLOTS="0")):
+        for key in ("SB2_KNN_EST", "SB2_KNN_TIERS", "SB2_KNN_LIST", "SB2_KNN_SCAN_SLOTS"):
             monkeypatch.delenv(key, raising=False)
         for key, val in env.items():
             monkeypatch.setenv(key, val)
         idx2, dist2, _ = _ops.knn(x, k)
         assert (idx2 == idx).all() and (dist2 == dist).all(), env
+
+
+def test_knn_resweep_tier_far_from_origin(monkeypatch):
+    # data far from the origin: the fp16 tier's rounding bound (|dq| R + |q| max|dc|) swamps the neighbour gaps, so
+    # rows fall through to the gathered split-precision re-sweep (forced here even for few rows) and stay exact
+    monkeypatch.setenv("SB2_KNN_SCAN_SLOTS", "0")
+    rs = np.random.RandomState(9)
+    y = (rs.standard_normal((6000, 24)) * 0.05 + 40.0).astype(np.float32)
+    idx, dist, info = _ops.knn(y, 15)
+    assert info["n_resweep"] > 0
+    oi, od = oknn.knn_brute(y, 15)
+    assert oknn.same_neighbor_sets(idx, dist, oi, od).all()
+    np.testing.assert_allclose(dist[:, 1:], od[:, 1:], rtol=1e-6, atol=1e-7)
 
 
 def test_knn_duplicates_zero_rows_and_scale():
