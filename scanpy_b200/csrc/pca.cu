@@ -215,47 +215,56 @@ right_mult_kernel(const double* __restrict__ A, const double* __restrict__ M, in
   for (int k = 0; k < l; ++k) s = fma(A[(size_t)r * l + k], sm[k * lo + c], s);
   C[o] = s;
 }
-// Z[g x l] = C[g x g] * V[g x l]   (C symmetric, dense fp64)
+// Z[g x l] += C[g x g] * V[g x l]   (C symmetric, dense fp64; Z zeroed by the caller)
+// 64 x 64 output tile per CTA, 4 x 4 per thread (16 FMA per 4 LDS.128), the K axis split over gridDim.y CTAs that
+// merge with fp64 REDs: 256 CTAs for g = 2000, l = 64 instead of 125 LDS-bound ones.
+constexpr int DSA_T = 64, DSA_K = 16, DSA_PAD = 66;
 __global__ void __launch_bounds__(256)
-dense_sym_apply_kernel(const double* __restrict__ C, const double* __restrict__ V, int g, int l, double* __restrict__ Z) {
-  constexpr int TR = 16, TK = 32;
-  extern __shared__ double sm[];  // Cs[TR][TK], Vs[TK][l]
-  double* Cs = sm;
-  double* Vs = sm + TR * TK;
-  const int r0 = blockIdx.x * TR;
-  // each thread owns outputs o = threadIdx.x + m*256 of the TR x l tile
-  double acc[8];
+dense_sym_apply_kernel(const double* __restrict__ C, const double* __restrict__ V, int g, int l, int k_per_split,
+                       double* __restrict__ Z) {
+  __shared__ __align__(16) double Cs[DSA_K][DSA_PAD];  // k-major: Cs[k][row]
+  __shared__ __align__(16) double Vs[DSA_K][DSA_T];
+  const int r0 = blockIdx.x * DSA_T, c0 = blockIdx.z * DSA_T;
+  const int kb = blockIdx.y * k_per_split, ke = min(g, kb + k_per_split);
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  double acc[4][4];
 #pragma unroll
-  for (int m = 0; m < 8; ++m) acc[m] = 0.0;
-  for (int k0 = 0; k0 < g; k0 += TK) {
-    for (int i = threadIdx.x; i < TR * TK; i += blockDim.x) {
-      const int r = i / TK, k = i % TK;
-      Cs[i] = (r0 + r < g && k0 + k < g) ? C[(size_t)(r0 + r) * g + k0 + k] : 0.0;
-    }
-    for (int i = threadIdx.x; i < TK * l; i += blockDim.x) {
-      const int k = i / l;
-      Vs[i] = (k0 + k < g) ? V[(size_t)(k0 + k) * l + (i % l)] : 0.0;
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.0;
+  for (int k0 = kb; k0 < ke; k0 += DSA_K) {
+#pragma unroll
+    for (int it = 0; it < 4; ++it) {
+      const int i = threadIdx.x + it * 256;
+      const int r = i >> 4, k = i & 15;  // 16 consecutive k of one row: 128 B per half-warp
+      Cs[k][r] = (r0 + r < g && k0 + k < ke) ? C[(size_t)(r0 + r) * g + k0 + k] : 0.0;
+      const int vk = i >> 6, vc = i & 63;
+      Vs[vk][vc] = (k0 + vk < ke && c0 + vc < l) ? V[(size_t)(k0 + vk) * l + c0 + vc] : 0.0;
     }
     __syncthreads();
 #pragma unroll
-    for (int m = 0; m < 8; ++m) {
-      const int o = threadIdx.x + m * 256;
-      if (o < TR * l) {
-        const int r = o / l, c = o % l;
-        double s = acc[m];
-#pragma unroll 8
-        for (int k = 0; k < TK; ++k) s = fma(Cs[r * TK + k], Vs[k * l + c], s);
-        acc[m] = s;
-      }
+    for (int k = 0; k < DSA_K; ++k) {
+      const double2 a01 = *reinterpret_cast<const double2*>(&Cs[k][ty * 4]);
+      const double2 a23 = *reinterpret_cast<const double2*>(&Cs[k][ty * 4 + 2]);
+      const double2 b01 = *reinterpret_cast<const double2*>(&Vs[k][tx * 4]);
+      const double2 b23 = *reinterpret_cast<const double2*>(&Vs[k][tx * 4 + 2]);
+      const double a[4] = {a01.x, a01.y, a23.x, a23.y};
+      const double bb[4] = {b01.x, b01.y, b23.x, b23.y};
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fma(a[i], bb[j], acc[i][j]);
     }
     __syncthreads();
   }
 #pragma unroll
-  for (int m = 0; m < 8; ++m) {
-    const int o = threadIdx.x + m * 256;
-    if (o < TR * l) {
-      const int r = o / l, c = o % l;
-      if (r0 + r < g) Z[(size_t)(r0 + r) * l + c] = acc[m];
+  for (int i = 0; i < 4; ++i) {
+    const int r = r0 + ty * 4 + i;
+    if (r >= g) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int c = c0 + tx * 4 + j;
+      if (c < l) atomicAdd(&Z[(size_t)r * l + c], acc[i][j]);
     }
   }
 }
@@ -573,8 +582,14 @@ int32_t apply_operator_spmm(PcaWork& w, const double* V, double* Z) {
 // Z = A_op * V  (V, Z device g x l fp64); A_op = X_c^T X_c summed over all ranks
 int32_t apply_operator(PcaWork& w, const double* V, double* Z) {
   if (w.solver == 1) {
-    dense_sym_apply_kernel<<<(unsigned)ceil_div64(w.g, 16), 256, sizeof(double) * (16 * 32 + 32 * w.l), w.st>>>(
-        w.d_C, V, w.g, w.l, Z);
+    // split K so that the grid covers the machine about twice over (fp64 REDs merge the partial tiles)
+    const int row_tiles = (int)ceil_div64(w.g, DSA_T), col_tiles = (int)ceil_div64(w.l, DSA_T);
+    int ksplit = std::max(1, (2 * w.ctx->prop.multiProcessorCount) / (row_tiles * col_tiles));
+    ksplit = std::min(ksplit, (int)ceil_div64(w.g, 4 * DSA_K));
+    const int k_per_split = (int)ceil_div64(ceil_div64(w.g, ksplit), DSA_K) * DSA_K;
+    SB2_CUDA(cudaMemsetAsync(Z, 0, sizeof(double) * (size_t)w.g * w.l, w.st));
+    dense_sym_apply_kernel<<<dim3((unsigned)row_tiles, (unsigned)ceil_div64(w.g, k_per_split), (unsigned)col_tiles), 256, 0, w.st>>>(
+        w.d_C, V, w.g, w.l, k_per_split, Z);
     SB2_LAUNCH_CHECK(w.ctx);
     return SB2_OK;
   }
@@ -724,8 +739,6 @@ int32_t sb2_pca_csr_f32(sb2_ctx* ctx, int64_t n, int64_t n_total, int32_t g, con
     }
     center_gram_kernel<<<(unsigned)ceil_div64((int64_t)gp * gp, 256), 256, 0, st>>>(w.d_C, w.d_mu, nt, gp);
     SB2_LAUNCH_CHECK(ctx);
-    SB2_CUDA(cudaFuncSetAttribute(dense_sym_apply_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  (int)(sizeof(double) * (16 * 32 + 32 * l))));
   } else {
     SB2_TRY(scr.alloc(&w.d_shift, (size_t)l));
     SB2_TRY(scr.alloc(&w.d_Y, (size_t)std::max<int64_t>(n, 1) * l));
