@@ -135,17 +135,16 @@ decide_kernel(Level L, const int32_t* __restrict__ comm, const int32_t* __restri
         w = L.w[e0 + lane];
       }
     }
-    int64_t tot = 0;
-    bool leader = true;
-#pragma unroll
-    for (int s = 0; s < 32; ++s) {
-      const int32_t cs = __shfl_sync(0xffffffffu, c, s);
-      const int64_t ws = __shfl_sync(0xffffffffu, w, s);
-      if (cs == c) {
-        tot += ws;
-        if (s < lane) leader = false;
-      }
-    }
+    // lanes that look at the same community form a group (MATCH.ANY); the group's arc weights - non-negative
+    // 2^-32 fixed point, < 2^63 in total - are summed exactly with three 24-bit-limb warp reductions (REDUX) instead
+    // of 32 rounds of shuffles
+    const unsigned grp = __match_any_sync(0xffffffffu, c);
+    const bool leader = (__ffs(grp) - 1) == lane;
+    const u64 uw = (u64)w;
+    const unsigned s0 = __reduce_add_sync(grp, (unsigned)(uw & 0xFFFFFFull));
+    const unsigned s1 = __reduce_add_sync(grp, (unsigned)((uw >> 24) & 0xFFFFFFull));
+    const unsigned s2 = __reduce_add_sync(grp, (unsigned)(uw >> 48));
+    const int64_t tot = (int64_t)((u64)s0 + ((u64)s1 << 24) + ((u64)s2 << 48));
     if (c >= 0 && leader) {
       if (!REFINE && c == a) wa = (double)tot;
       else if (allowed(c)) { best_gain = (double)tot - scale * (double)K[c]; best = c; }
