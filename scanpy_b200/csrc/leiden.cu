@@ -370,10 +370,6 @@ __global__ void internal_weight_kernel(int32_t n, const int64_t* __restrict__ in
   for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
   if ((threadIdx.x & 31) == 0 && s != 0) atomicAdd(internal, (u64)s);
 }
-__global__ void comm_min_member_kernel(int64_t n, const int32_t* __restrict__ comm, int32_t* __restrict__ minmem) {
-  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) atomicMin(&minmem[comm[i]], (int32_t)i);
-}
 __global__ void relabel_kernel(int64_t n, int32_t* __restrict__ comm, const int32_t* __restrict__ newid) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) comm[i] = newid[comm[i]];
