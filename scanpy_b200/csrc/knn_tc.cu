@@ -1,30 +1,34 @@
-// knn_tc.cu — tensor-core first pass of the exact kNN (sm_100a: tcgen05.mma + TMEM + bulk-copy ring).
+// knn_tc.cu — tensor-core sweeps of the exact kNN (sm_100a: tcgen05.mma + TMEM + bulk-copy ring).
 //
-// Same contract as knn_pass1_kernel (knn.cu): per query keep 32 proposals whose score
+// Contract (shared with knn_pass1_kernel in knn.cu): per query keep the list_m (32 or 64) proposals whose score
 //     s(q,c) = q.c - |c|^2/2        (d^2 = |q|^2 - 2 s)
-// is largest, plus a rigorous bound on the rounding error of s, so that knn_rescore_kernel can certify
-// the exact fp64 top-k.  The GEMM-shaped middle term runs on the 5th-gen tensor cores in split
-// precision: every fp32 coordinate x (scaled by a power of two) is written as hi + lo with
-// hi = fp16(x), lo = fp16(x - hi) (22 significant bits), and
-//     q.c ~= q_hi.c_hi + q_hi.c_lo + q_lo.c_hi
-// is ONE fp16 MMA over a concatenated K axis  A = [q_hi | q_hi | q_lo | 1 1 1],
-// B = [c_hi | c_lo | c_hi | h0 h1 h2]  with h0+h1+h2 = -|c|^2/2 (three-way fp16 split), fp32
-// accumulation in TMEM.  K = 3d+3 padded to a multiple of 16 (d = 50 -> 160: ten k-steps).
+// is largest, plus a rigorous bound on the rounding error of s, so that knn_rescore_kernel can certify the exact
+// fp64 top-k.  The GEMM-shaped middle term runs on the 5th-gen tensor cores, fp32 accumulation in TMEM, in one of
+// two operand formats (coordinates scaled by a power of two so that max|x| is in [100, 200)):
+//   terms = 1  fp16 operands            A = [q_hi | 1 1 1],             B = [c_hi | h0 h1 h2]            K = d+3
+//   terms = 3  split fp16 (22 bits)     A = [q_hi | q_hi | q_lo | 1 1 1], B = [c_hi | c_lo | c_hi | h0 h1 h2]  K = 3d+3
+// with hi = fp16(x), lo = fp16(x - hi) and h0+h1+h2 = -|c|^2/2 (three-way fp16 split); K is padded to a multiple
+// of 16 (d = 50: 64 and 160).  knn.cu runs terms = 1 first and re-sweeps the rows it cannot certify with terms = 3.
 //
-// knn_tc_prep_kernel   X[n,d] -> per 128-point tile one A image and one B image, stored exactly as the
-//                      UMMA "no-swizzle, K-major" shared-memory layout wants them (8x8 fp16 core
-//                      matrices; K-chunk-major), so a tile is staged by ONE 1-D bulk (TMA) copy.
-// knn_pass1_tc_kernel  CTA = 256 queries (two M=128 halves) x all candidate tiles (N=128 each).
-//                      warp 0   : producer, cp.async.bulk ring (3 stages x 40 KB) on mbarriers
-//                      warp 1   : TMEM allocator + single-thread tcgen05.mma issuer; per candidate tile
-//                                 2 x 10 MMAs (128x128x16) into one of two 256-column accumulator
-//                                 buffers; tcgen05.commit releases the smem stage and publishes the buffer
-//                      warps 2-9: epilogue; thread <-> one query row (TMEM lane); tcgen05.ld 32 columns
-//                                 at a time, one FSETP per element against the row's 32nd-best score;
-//                                 survivors (~300 per row over the whole sweep) go to the row's
-//                                 32-entry list in global memory (L2-resident, replace-the-minimum).
-// Candidate images are re-read by every CTA from L2: 40 KB per 256x128 tile pair => ~5 TB/s at the
-// tensor-pipe rate; 256 queries per CTA (not 128) is what keeps that under the L2 bandwidth.
+// knn_tc_prep_kernel   X[n,d] -> per 128-point tile one A image and/or one B image, stored exactly as the UMMA
+//                      "no-swizzle, K-major" shared-memory layout wants them (8x8 fp16 core matrices, K-chunk-major),
+//                      so a tile (or a K-slice of it) is staged by ONE 1-D bulk (TMA) copy; optionally gathers the
+//                      rows (re-sweep) and records each point's fp16 residual norm |x - fp16(x)| (terms = 1 bound).
+// knn_pass1_tc_kernel  CTA = 256 queries (two M=128 halves; 128 queries for wide K) x all candidate tiles (N=128).
+//                      warp 0     : producer, cp.async.bulk ring on mbarriers (as many stages as shared memory holds)
+//                      warps 1,10 : MMA issuers, one per query half: whole-warp loop, elect.sync inside the asm block,
+//                                   operands on the uniform datapath -> back-to-back UTCHMMA; tcgen05.commit releases
+//                                   the smem stage and publishes (accumulator buffer, half); warp 1 owns TMEM
+//                                   (alloc, teardown - no CTA-wide barrier after the role branches)
+//                      warps 2-9  : epilogue; thread <-> one query row (TMEM lane); two tcgen05.ld of 32 columns in
+//                                   flight, a two-level FMNMX3 tree + one compare per 32 values against the row's
+//                                   threshold; survivors go to the row's register-resident list (ids to global
+//                                   memory, write-only); the accumulator slab is released after its second load
+//                                   round trip.  The first visits sweep every 16th tile and only keep the 6 largest
+//                                   chunk maxima per row: the 6th seeds the threshold (rank ~96), so the sweep proper
+//                                   sees ~60 insertions per row instead of ~340.
+// Candidate images are re-read by every CTA from L2 (16 KB per 256x128 score tile for d = 50, 97 % L2 hits).
+// DESIGN.md section 4 has the measurements behind each of these choices.
 #include <cuda_fp16.h>
 #include <float.h>
 
