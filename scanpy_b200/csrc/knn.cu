@@ -319,6 +319,13 @@ __global__ void knn_rescore_kernel(const float* __restrict__ X, int64_t n_points
     }
     const double bound = qn - 2.0 * ((double)smin * (inv_s2 ? (double)*inv_s2 : 1.0) + eps);
     certified = self_first && (kth < bound);
+    if (inv_s2) {
+      // the tensor-path bounds are derived for a scaled largest norm in [100, 200) (knn_tc_prep_kernel's power-of-two
+      // scale); data so tiny or so huge that the clamped scale cannot reach it (largest norm below ~1e-16 or above
+      // ~2e20) is left to the exact scan.  Also catches non-finite scores.
+      const double r2s2 = Rn * Rn / (double)*inv_s2;
+      if (!(r2s2 >= 9801.0 && r2s2 <= 67600.0)) certified = false;
+    }
   }
 #pragma unroll
   for (int r = 0; r < R; ++r) {
