@@ -165,3 +165,36 @@ def test_rename_groups_matches_reference():
     assert out.tolist() == ["0", "1,0", "1,1", "2", "1,0", "0"]
     with pytest.raises(ValueError, match="not a valid category"):
         tl._restrict_adjacency(a, "louvain", restrict_categories=["9"], adjacency=adj)
+
+
+def test_struct_layouts_match_the_header(tmp_path):
+    """The ctypes mirrors of the info structs (scanpy_b200/_abi.py) must have the size and field offsets a C compiler
+    gives include/scanpy_b200.h - the header is the contract a reference-side binding would be written against."""
+    import ctypes
+    import shutil
+    import subprocess
+
+    from scanpy_b200 import _abi
+
+    if shutil.which("gcc") is None:
+        pytest.skip("gcc not available")
+    root = Path(__file__).resolve().parents[1]
+    structs = {"sb2_device_info": _abi.DeviceInfo, "sb2_pca_info": _abi.PcaInfo, "sb2_knn_info": _abi.KnnInfo,
+               "sb2_leiden_info": _abi.LeidenInfo}
+    lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "scanpy_b200.h"', "int main(void) {"]
+    for cname, cls in structs.items():
+        lines.append(f'  printf("{cname} %zu", sizeof({cname}));')
+        for fname, _ in cls._fields_:
+            lines.append(f'  printf(" %zu", offsetof({cname}, {fname}));')
+        lines.append('  printf("\\n");')
+    lines += ["  return 0;", "}"]
+    src = tmp_path / "layout.c"
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "layout"
+    subprocess.run(["gcc", "-I", str(root / "include"), str(src), "-o", str(exe)], check=True)
+    out = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.strip().splitlines()
+    for line, (cname, cls) in zip(out, structs.items()):
+        parts = line.split()
+        assert parts[0] == cname
+        assert int(parts[1]) == ctypes.sizeof(cls), cname
+        assert [int(x) for x in parts[2:]] == [getattr(cls, f).offset for f, _ in cls._fields_], cname
