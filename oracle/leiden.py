@@ -31,6 +31,9 @@ def _load():
         lib.leiden_ref.restype = ctypes.c_int
         lib.leiden_ref.argtypes = [ctypes.c_int32, P, P, P, ctypes.c_double, ctypes.c_int32, ctypes.c_uint64,
                                    P, P, P, P]
+        lib.leiden_ref2.restype = ctypes.c_int
+        lib.leiden_ref2.argtypes = [ctypes.c_int32, P, P, P, ctypes.c_double, ctypes.c_int32, ctypes.c_uint64, ctypes.c_double,
+                                    P, P, P, P]
         lib.modularity_ref.restype = ctypes.c_double
         lib.modularity_ref.argtypes = [ctypes.c_int32, P, P, P, ctypes.c_double, P]
         _lib = lib
@@ -45,17 +48,21 @@ def _csr_args(adj):
     return adj.shape[0], indptr, indices, w
 
 
-def leiden(adj, *, resolution: float = 1.0, n_iterations: int = -1, seed: int = 0):
-    """-> (membership int32[n] renumbered by decreasing size, modularity at `resolution`, n_passes)."""
+def leiden(adj, *, resolution: float = 1.0, n_iterations: int = -1, seed: int = 0, beta: float = 0.0):
+    """-> (membership int32[n] renumbered by decreasing size, modularity at `resolution`, n_passes).
+
+    beta = 0: greedy refinement, what leidenalg's optimiser does for scanpy's flavor='leidenalg';
+    beta > 0: the paper's randomised refinement over well-connected vertices/communities, what igraph's
+    community_leiden does for flavor='igraph' (scanpy passes igraph's default beta = 0.01)."""
     lib = _load()
     n, indptr, indices, w = _csr_args(adj)
     member = np.empty(n, np.int32)
     q = ctypes.c_double()
     nc = ctypes.c_int32()
     passes = ctypes.c_int32()
-    rc = lib.leiden_ref(n, indptr.ctypes.data, indices.ctypes.data, w.ctypes.data, float(resolution),
-                        int(n_iterations), int(seed), member.ctypes.data, ctypes.addressof(q),
-                        ctypes.addressof(nc), ctypes.addressof(passes))
+    rc = lib.leiden_ref2(n, indptr.ctypes.data, indices.ctypes.data, w.ctypes.data, float(resolution),
+                         int(n_iterations), int(seed), float(beta), member.ctypes.data, ctypes.addressof(q),
+                         ctypes.addressof(nc), ctypes.addressof(passes))
     assert rc == 0
     return member, q.value, passes.value
 

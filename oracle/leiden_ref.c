@@ -17,6 +17,8 @@
  * C ABI (ctypes, see oracle/leiden.py):
  *   int leiden_ref(n, indptr[int64 n+1], indices[int32], weights[double], gamma, n_iterations, seed,
  *                  membership_out[int32 n], modularity_out[double], n_comms_out[int32], passes_out[int32])
+ *   int leiden_ref2(..., seed, beta, ...)   beta <= 0: greedy refinement (leidenalg); beta > 0: randomised refinement
+ *                  restricted to well-connected vertices / communities (the paper; igraph uses beta = 0.01)
  *   double modularity_ref(n, indptr, indices, weights, gamma, membership)
  * The input must be a symmetric adjacency in CSR (both (i,j) and (j,i) stored); a diagonal entry A_ii
  * counts as sum_{i,j in c} contribution A_ii (this is how aggregated self-loops are stored).
@@ -117,14 +119,36 @@ static int64_t move_nodes(const graph_t *g, int32_t *comm, double *K, int32_t *c
   return moves;
 }
 
-/* Refinement: singletons merge greedily into refined communities inside their parent community. */
-static void merge_nodes_constrained(const graph_t *g, const int32_t *parent, int32_t *ref, double gamma) {
+static double rng_uniform(void) { return (double)(rng_next() >> 11) * (1.0 / 9007199254740992.0); }
+
+/* Refinement: singletons merge into refined communities inside their parent community.
+ *   beta <= 0  leidenalg's Optimiser::merge_nodes_constrained as scanpy's flavor='leidenalg' runs it (default
+ *              refine_consider_comms = ALL_NEIGH_COMMS): the best non-negative gain wins, greedy, no connectivity test.
+ *   beta  > 0  the published algorithm (Traag, Waltman & van Eck 2019, section "Refinement") as igraph's
+ *              community_leiden runs it for scanpy's flavor='igraph' (beta = 0.01): only a singleton v that is well
+ *              connected to its parent community S,  E(v, S-v) >= gamma k_v (K_S - k_v) / 2m,  moves; only into a refined
+ *              community C that is itself well connected,  E(C, S-C) >= gamma K_C (K_S - K_C) / 2m,  with a non-negative
+ *              gain; the target is drawn with probability ~ exp(gain / beta). */
+static void merge_nodes_constrained(const graph_t *g, const int32_t *parent, int32_t *ref, double gamma, double beta) {
   const int32_t n = g->n;
   double *K = (double *)malloc(sizeof(double) * (size_t)n);
   int32_t *csize = (int32_t *)malloc(sizeof(int32_t) * (size_t)n);
   int32_t *order = (int32_t *)malloc(sizeof(int32_t) * (size_t)n);
   double *cw = (double *)calloc((size_t)n, sizeof(double));
   int32_t *touched = (int32_t *)malloc(sizeof(int32_t) * (size_t)n);
+  double *Kpar = NULL, *ext = NULL, *prob = NULL;
+  if (beta > 0.0) {
+    Kpar = (double *)calloc((size_t)n, sizeof(double));   /* strength of each parent community */
+    ext = (double *)calloc((size_t)n, sizeof(double));    /* E(C, S-C) per refined community */
+    prob = (double *)malloc(sizeof(double) * (size_t)n);
+    for (int32_t i = 0; i < n; ++i) {
+      Kpar[parent[i]] += g->k[i];
+      for (int64_t e = g->indptr[i]; e < g->indptr[i + 1]; ++e) {
+        int32_t u = g->indices[e];
+        if (u != i && parent[u] == parent[i]) ext[i] += g->w[e];
+      }
+    }
+  }
   for (int32_t i = 0; i < n; ++i) { ref[i] = i; K[i] = g->k[i]; csize[i] = 1; order[i] = i; }
   shuffle(order, n);
   const double inv2m = 1.0 / g->total;
@@ -132,6 +156,7 @@ static void merge_nodes_constrained(const graph_t *g, const int32_t *parent, int
     int32_t v = order[ii];
     if (csize[ref[v]] != 1) continue; /* only singletons move */
     const double kv = g->k[v];
+    if (beta > 0.0 && ext[ref[v]] < gamma * kv * (Kpar[parent[v]] - kv) * inv2m - 1e-15) continue; /* v not well connected */
     int32_t nt = 0;
     for (int64_t e = g->indptr[v]; e < g->indptr[v + 1]; ++e) {
       int32_t u = g->indices[e];
@@ -140,21 +165,46 @@ static void merge_nodes_constrained(const graph_t *g, const int32_t *parent, int
       if (cw[c] == 0.0) touched[nt++] = c;
       cw[c] += g->w[e];
     }
-    double best_gain = 0.0; /* staying alone: w=0, K(without v)=0 */
     int32_t best = ref[v];
-    for (int32_t t = 0; t < nt; ++t) {
-      int32_t c = touched[t];
-      double gain = cw[c] - gamma * kv * K[c] * inv2m;
-      if (gain > best_gain + 1e-15 || (best != ref[v] && fabs(gain - best_gain) <= 1e-15 && c < best)) {
-        best_gain = gain; best = c;
+    if (beta <= 0.0) {
+      double best_gain = 0.0; /* staying alone: w=0, K(without v)=0 */
+      for (int32_t t = 0; t < nt; ++t) {
+        int32_t c = touched[t];
+        double gain = cw[c] - gamma * kv * K[c] * inv2m;
+        if (gain > best_gain + 1e-15 || (best != ref[v] && fabs(gain - best_gain) <= 1e-15 && c < best)) {
+          best_gain = gain; best = c;
+        }
       }
+    } else {
+      /* candidates: staying alone (gain 0) and every well-connected neighbouring refined community with gain >= 0 */
+      double max_gain = 0.0, total_p = 0.0;
+      int32_t ncand = 0;
+      for (int32_t t = 0; t < nt; ++t) {
+        int32_t c = touched[t];
+        if (c == ref[v]) continue;
+        if (ext[c] < gamma * K[c] * (Kpar[parent[v]] - K[c]) * inv2m - 1e-15) continue;
+        double gain = cw[c] - gamma * kv * K[c] * inv2m;
+        if (gain < 0.0) continue;
+        touched[ncand] = c; prob[ncand] = gain; ++ncand;   /* compacts in place: ncand <= t */
+        if (gain > max_gain) max_gain = gain;
+      }
+      /* cw of dropped candidates must still be cleared below: remember them through a second pass over the arcs */
+      for (int32_t t = 0; t < ncand; ++t) { prob[t] = exp((prob[t] - max_gain) / beta); total_p += prob[t]; }
+      const double p_stay = exp((0.0 - max_gain) / beta);
+      total_p += p_stay;
+      double r = rng_uniform() * total_p;
+      best = ref[v];
+      for (int32_t t = 0; t < ncand; ++t) { if (r < prob[t]) { best = touched[t]; break; } r -= prob[t]; }
     }
-    for (int32_t t = 0; t < nt; ++t) cw[touched[t]] = 0.0;
+    const double w_best = (best != ref[v]) ? cw[best] : 0.0;
+    for (int64_t e = g->indptr[v]; e < g->indptr[v + 1]; ++e) cw[ref[g->indices[e]]] = 0.0;
     if (best != ref[v]) {
+      if (beta > 0.0) { ext[best] += ext[ref[v]] - 2.0 * w_best; ext[ref[v]] = 0.0; }
       K[ref[v]] -= kv; csize[ref[v]]--; K[best] += kv; csize[best]++; ref[v] = best;
     }
   }
   free(K); free(csize); free(order); free(cw); free(touched);
+  if (Kpar) { free(Kpar); free(ext); free(prob); }
 }
 
 /* relabel labels[] to 0..nc-1 (first-occurrence order); returns nc */
@@ -227,7 +277,7 @@ static double quality(const graph_t *g, const int32_t *comm, double gamma) {
 
 /* One leidenalg-style optimise_partition pass on the ORIGINAL graph g0, starting from member0[] (values < n).
  * Returns 1 if any node moved. */
-static int optimise_pass(const graph_t *g0, int32_t *member0, double gamma) {
+static int optimise_pass(const graph_t *g0, int32_t *member0, double gamma, double beta) {
   const int32_t n0 = g0->n;
   graph_t g = *g0; /* current level graph (level 0 borrows g0's arrays) */
   int level0 = 1, improved = 0;
@@ -246,7 +296,7 @@ static int optimise_pass(const graph_t *g0, int32_t *member0, double gamma) {
     /* push the level's communities down to the original nodes */
     for (int32_t i = 0; i < n0; ++i) member0[i] = comm[node_of[i]];
     int32_t *ref = (int32_t *)malloc(sizeof(int32_t) * (size_t)n);
-    merge_nodes_constrained(&g, comm, ref, gamma);
+    merge_nodes_constrained(&g, comm, ref, gamma, beta);
     int32_t nc = compact_labels(ref, n);
     /* number of (non-empty) communities at this level */
     int32_t *tmp = (int32_t *)malloc(sizeof(int32_t) * (size_t)n);
@@ -297,9 +347,9 @@ static int32_t renumber_by_size(int32_t *member, int32_t n) {
   return nc;
 }
 
-int leiden_ref(int32_t n, const int64_t *indptr, const int32_t *indices, const double *weights, double gamma,
-               int32_t n_iterations, uint64_t seed, int32_t *membership, double *modularity, int32_t *n_comms,
-               int32_t *passes) {
+int leiden_ref2(int32_t n, const int64_t *indptr, const int32_t *indices, const double *weights, double gamma,
+                int32_t n_iterations, uint64_t seed, double beta, int32_t *membership, double *modularity, int32_t *n_comms,
+                int32_t *passes) {
   graph_t g; g.n = n; g.indptr = (int64_t *)indptr; g.indices = (int32_t *)indices; g.w = (double *)weights;
   graph_strengths(&g);
   rng_state = seed * 0x9E3779B97F4A7C15ULL + 0x1234567ULL;
@@ -307,7 +357,7 @@ int leiden_ref(int32_t n, const int64_t *indptr, const int32_t *indices, const d
   int32_t it = 0;
   if (g.total > 0.0) {
     for (;;) {
-      int improved = optimise_pass(&g, membership, gamma);
+      int improved = optimise_pass(&g, membership, gamma, beta);
       ++it;
       compact_labels(membership, n);
       if (n_iterations >= 0 ? it >= n_iterations : !improved) break;
@@ -318,6 +368,12 @@ int leiden_ref(int32_t n, const int64_t *indptr, const int32_t *indices, const d
   *passes = it;
   free(g.k);
   return 0;
+}
+
+int leiden_ref(int32_t n, const int64_t *indptr, const int32_t *indices, const double *weights, double gamma,
+               int32_t n_iterations, uint64_t seed, int32_t *membership, double *modularity, int32_t *n_comms,
+               int32_t *passes) {
+  return leiden_ref2(n, indptr, indices, weights, gamma, n_iterations, seed, 0.0, membership, modularity, n_comms, passes);
 }
 
 double modularity_ref(int32_t n, const int64_t *indptr, const int32_t *indices, const double *weights,

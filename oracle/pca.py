@@ -61,3 +61,43 @@ def align_signs(a: np.ndarray, b: np.ndarray) -> np.ndarray:
     s = np.sign(np.einsum("ij,ij->j", a, b))
     s[s == 0] = 1
     return a * s
+
+
+def gram_f64_blocked(x, *, block_rows: int = 16384):
+    """(G = X^T X, column sums), both in float64, for a scipy CSR matrix, by dense row blocks through BLAS (a sparse-sparse product
+    costs sum_r nnz_r^2 hashed updates on one core; densified syrk blocks use every core).  This is the host-side
+    restatement of the reference's `csr_gram_dense` (src/scanpy/preprocessing/_pca/_kernels.py:14-58)."""
+    n, g = x.shape
+    gram = np.zeros((g, g), np.float64)
+    colsum = np.zeros(g, np.float64)
+    for r0 in range(0, n, block_rows):
+        blk = x[r0:r0 + block_rows].toarray().astype(np.float64, copy=False)
+        gram += blk.T @ blk
+        colsum += blk.sum(axis=0)
+    return gram, colsum
+
+
+def pca_gram_f64(x, n_comps: int, *, rows=None):
+    """Float64 ground truth through the covariance_eigh route (src/scanpy/preprocessing/_pca/_dask.py:143-213
+    restated with ddof=1 like sklearn's explained_variance_): Gram -> covariance -> LAPACK eigh -> projection.
+    Never densifies more than a row block, so it also serves the 100k and 1.3M configurations.
+    `rows`: project only these rows (X_pca of a sample); None = all rows."""
+    import scipy.linalg as sla
+
+    n, g = x.shape
+    gram, colsum = gram_f64_blocked(x)
+    mu = colsum / n
+    cov = (gram - n * np.outer(mu, mu)) / (n - 1)
+    w, v = sla.eigh(cov, subset_by_index=[g - n_comps, g - 1])
+    w, v = w[::-1], v[:, ::-1]
+    vt = v.T.copy()
+    sign = np.sign(vt[np.arange(n_comps), np.argmax(np.abs(vt), axis=1)])
+    vt *= sign[:, None]
+    xs = x if rows is None else x[np.asarray(rows)]
+    x_pca = np.asarray(xs.astype(np.float64) @ vt.T) - mu @ vt.T
+    total_var = float(np.trace(cov))
+    # relative spectrum gaps (sigma_j - sigma_{j+1}) / sigma_j of the singular values, one more than n_comps
+    w_all = sla.eigh(cov, subset_by_index=[g - n_comps - 1, g - 1], eigvals_only=True)[::-1]
+    s = np.sqrt(np.maximum(w_all, 0.0))
+    gaps = (s[:-1] - s[1:]) / s[:-1]
+    return dict(X_pca=x_pca, components=vt, variance=w, variance_ratio=w / total_var, mean=mu, gaps=gaps)

@@ -95,6 +95,8 @@ def pca_csr(x, n_comps: int, *, solver: int = 0, max_iter: int = 0, tol: float =
 # ------------------------------------------------------------------------------------------ kNN
 def knn_device(ctx, d_x, n_neighbors: int, *, q0: int = 0, n_query: int | None = None):
     torch = _torch()
+    if d_x.dtype != torch.float32 or not d_x.is_contiguous() or d_x.dim() != 2:
+        raise TypeError("knn_device expects a contiguous 2-D float32 CUDA tensor")
     n, d = d_x.shape
     n_query = n - q0 if n_query is None else n_query
     idx = torch.empty((n_query, n_neighbors), dtype=torch.int32, device="cuda")
@@ -176,6 +178,7 @@ def knn_and_connectivities(x: np.ndarray, n_neighbors: int, *, ctx=None):
     from scipy import sparse
 
     ctx = ctx or _abi.default_context()
+    x = np.ascontiguousarray(x, dtype=np.float32)  # the kernel reads float32 rows: never reinterpret another dtype
     n = x.shape[0]
     d_x = _to_device(x)
     d_idx, d_dist, _ = knn_device(ctx, d_x, n_neighbors)

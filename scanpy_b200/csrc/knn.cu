@@ -227,12 +227,15 @@ __device__ __forceinline__ bool lex_less(double ka, int ia, double kb, int ib) {
   return ka < kb || (ka == kb && ia < ib);
 }
 
-// R = proposals per lane: the list has 32*R entries (R = 1: 32 proposals, k <= 24 keeps a slack of >= 8;
-// R = 2: 64 proposals for k up to 56)
+// R = proposals per lane: the list has 32*R entries.  The list is made of sub-lists of `sub` consecutive slots (sub = 32*R
+// for a single list; the second-generation tensor sweep keeps four sub-lists per row, one per column quarter of a
+// tile).  Every sub-list covers a disjoint part of the candidates and its smallest stored score (a real proposal or
+// the sentinel it started from) bounds the score of every candidate of that part that is NOT in it; hence no
+// unproposed candidate scored above tau = max over sub-lists of their minima.
 template <int R>
 __global__ void knn_rescore_kernel(const float* __restrict__ X, int64_t n_points, int d, int64_t q0, int64_t ql_base,
                                    const int32_t* __restrict__ row_map, int64_t n_rows,
-                                   int k, const float* __restrict__ cand_score, const int32_t* __restrict__ cand_idx,
+                                   int k, int sub, const float* __restrict__ cand_score, const int32_t* __restrict__ cand_idx,
                                    const unsigned int* __restrict__ maxnorm_bits, const float* __restrict__ inv_s2,
                                    double c_q, double c_n, const float* __restrict__ dnorm,
                                    const unsigned int* __restrict__ dmax_bits, int32_t* __restrict__ idx_out,
@@ -249,13 +252,12 @@ __global__ void knn_rescore_kernel(const float* __restrict__ X, int64_t n_points
   const float* xq = X + q * d;
   double key[R];
   int32_t id[R];
+  float cs[R];
   double qn = 0.0;
-  float smin = INFINITY;
-  bool all_used = true;
 #pragma unroll
   for (int r = 0; r < R; ++r) {
     const int32_t ci = cand_idx[li * LM + r * 32 + lane];
-    const float cs = cand_score[li * LM + r * 32 + lane];
+    cs[r] = cand_score[li * LM + r * 32 + lane];  // unused slots hold the sweep's starting threshold (-inf for a cold start)
     const float* xc = X + (int64_t)(ci < 0 ? 0 : ci) * d;
     double acc = 0.0, qq = 0.0;
     for (int j = 0; j < d; ++j) {
@@ -267,21 +269,49 @@ __global__ void knn_rescore_kernel(const float* __restrict__ X, int64_t n_points
     qn = qq;
     key[r] = ci < 0 ? DBL_MAX : ((ci == q) ? -1.0 : acc);
     id[r] = ci < 0 ? INT32_MAX : ci;
-    smin = fminf(smin, cs);  // unused slots hold the sweep's starting threshold (-inf for a cold start)
-    if (ci < 0) all_used = false;
+  }
+  // tau = max over sub-lists of (min over the sub-list's slots)
+  float tau = -INFINITY;
+  if (sub >= 32) {
+    const int regs_per = sub >> 5;
+#pragma unroll
+    for (int r0 = 0; r0 < R; ++r0) {
+      if (r0 % regs_per == 0) {
+        float m = INFINITY;
+#pragma unroll
+        for (int r = 0; r < R; ++r)
+          if (r >= r0 && r < r0 + regs_per) m = fminf(m, cs[r]);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) m = fminf(m, __shfl_xor_sync(0xffffffffu, m, o));
+        tau = fmaxf(tau, m);
+      }
+    }
+  } else {
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      float m = cs[r];
+      for (int o = sub >> 1; o > 0; o >>= 1) m = fminf(m, __shfl_xor_sync(0xffffffffu, m, o));   // min inside the sub-list's lanes
+      for (int o = 16; o >= sub; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));      // max across the sub-lists of this register
+      tau = fmaxf(tau, m);
+    }
   }
   // bitonic sort of the 32*R elements (element e = r*32 + lane) ascending by (key, id)
 #pragma unroll
   for (int kk = 2; kk <= LM; kk <<= 1) {
 #pragma unroll
     for (int j = kk >> 1; j > 0; j >>= 1) {
-      if (j >= 32) {  // partner lives in the same lane, other register (only R == 2, j == 32)
-        if (R == 2) {
-          const bool asc = true;  // kk == 64: final merge, ascending everywhere
-          const bool swap = lex_less(key[R - 1], id[R - 1], key[0], id[0]) == asc;
-          if (swap) {
-            const double tk = key[0]; key[0] = key[R - 1]; key[R - 1] = tk;
-            const int32_t ti = id[0]; id[0] = id[R - 1]; id[R - 1] = ti;
+      if (j >= 32) {  // partner lives in the same lane, register r ^ (j / 32)
+        const int rj = j >> 5;
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+          if ((r & rj) == 0 && (r | rj) < R) {
+            const int r2 = r | rj;
+            const bool asc = ((r * 32) & kk) == 0;
+            const bool swap = asc ? lex_less(key[r2], id[r2], key[r], id[r]) : lex_less(key[r], id[r], key[r2], id[r2]);
+            if (swap) {
+              const double tk = key[r]; key[r] = key[r2]; key[r2] = tk;
+              const int32_t ti = id[r]; id[r] = id[r2]; id[r2] = ti;
+            }
           }
         }
       } else {
@@ -301,15 +331,15 @@ __global__ void knn_rescore_kernel(const float* __restrict__ X, int64_t n_points
   // the query itself must sit in column 0 (src/scanpy/neighbors/_common.py:74-98); if it was not proposed at
   // all (a flood of exact duplicates can push it out of the list) the row is not certified.
   const bool self_first = __shfl_sync(0xffffffffu, id[0], 0) == (int32_t)q;
-  const double kth = (R == 1 || k <= 32) ? __shfl_sync(0xffffffffu, key[0], (k - 1) & 31)
-                                          : __shfl_sync(0xffffffffu, key[R - 1], (k - 1) & 31);
-  // worst proposal score (lists are unsorted) and whether all slots are in use
+  double kth = 0.0;
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) smin = fminf(smin, __shfl_xor_sync(0xffffffffu, smin, o));
-  const bool list_full = __all_sync(0xffffffffu, all_used);
+  for (int r = 0; r < R; ++r) {
+    const double t = __shfl_sync(0xffffffffu, key[r], (k - 1) & 31);
+    if (r == ((k - 1) >> 5)) kth = t;
+  }
   bool certified;
-  if (!list_full && smin == -INFINITY) {
-    certified = true;  // cold start and fewer than 32*R points exist: the proposal list is the whole data set
+  if (tau == -INFINITY) {
+    certified = true;  // cold start and no sub-list ever filled: the proposal list is the whole data set
   } else {
     const double Rn = sqrt((double)__uint_as_float(*maxnorm_bits));
     double eps = c_n * 0.5 * Rn * Rn + c_q * sqrt(qn) * Rn;
@@ -317,10 +347,10 @@ __global__ void knn_rescore_kernel(const float* __restrict__ X, int64_t n_points
       const double dq = (double)dnorm[q], dc = (double)__uint_as_float(*dmax_bits);
       eps += (dq * Rn + (sqrt(qn) + dq) * dc) * (1.0 + 1e-6);
     }
-    const double bound = qn - 2.0 * ((double)smin * (inv_s2 ? (double)*inv_s2 : 1.0) + eps);
+    const double bound = qn - 2.0 * ((double)tau * (inv_s2 ? (double)*inv_s2 : 1.0) + eps);
     certified = self_first && (kth < bound);
     if (inv_s2) {
-      // the tensor-path bounds are derived for a scaled largest norm in [100, 200) (knn_tc_prep_kernel's power-of-two
+      // the tensor-path bounds are derived for a scaled largest norm in [100, 200) (the prep kernel's power-of-two
       // scale); data so tiny or so huge that the clamped scale cannot reach it (largest norm below ~1e-16 or above
       // ~2e20) is left to the exact scan.  Also catches non-finite scores.
       const double r2s2 = Rn * Rn / (double)*inv_s2;
@@ -416,7 +446,9 @@ knn_fallback_kernel(const float* __restrict__ X, const float* __restrict__ Xt, i
         }
       }
       __syncthreads();
-      if (cnt > FB_BUF - FB_THREADS) {
+      const bool compact = cnt > FB_BUF - FB_THREADS;  // snapshot: every thread takes the same branch
+      __syncthreads();                                 // ... before anybody's next atomicAdd can change cnt
+      if (compact) {
         const int c0 = cnt;
         for (int i = c0 + threadIdx.x; i < FB_BUF; i += blockDim.x) { keys[i] = DBL_MAX; ids[i] = INT32_MAX; }
         __syncthreads();
@@ -475,7 +507,7 @@ struct EventPairs {  // CUDA-event brackets around the sweep kernels of one call
   }
 };
 
-int32_t launch_rescore(sb2_ctx* ctx, int list_m, const float* d_x, int64_t n_points, int d, int64_t q0, int64_t ql_base,
+int32_t launch_rescore(sb2_ctx* ctx, int list_m, int sub, const float* d_x, int64_t n_points, int d, int64_t q0, int64_t ql_base,
                        const int32_t* row_map, int64_t n_rows, int k, const float* cand_score, const int32_t* cand_idx,
                        const unsigned int* maxnorm, const float* inv_s2, double c_q, double c_n, const float* dnorm,
                        const unsigned int* dmax_bits, int32_t* d_idx,
@@ -483,12 +515,13 @@ int32_t launch_rescore(sb2_ctx* ctx, int list_m, const float* d_x, int64_t n_poi
   if (n_rows == 0) return SB2_OK;
   const int wpb = 8;
   const unsigned grid = (unsigned)ceil_div64(n_rows, wpb);
-  if (list_m == 32)
-    knn_rescore_kernel<1><<<grid, wpb * 32, 0, ctx->stream>>>(d_x, n_points, d, q0, ql_base, row_map, n_rows, k, cand_score,
-                                                               cand_idx, maxnorm, inv_s2, c_q, c_n, dnorm, dmax_bits, d_idx, d_dist, wq, wub, wcnt);
-  else
-    knn_rescore_kernel<2><<<grid, wpb * 32, 0, ctx->stream>>>(d_x, n_points, d, q0, ql_base, row_map, n_rows, k, cand_score,
-                                                               cand_idx, maxnorm, inv_s2, c_q, c_n, dnorm, dmax_bits, d_idx, d_dist, wq, wub, wcnt);
+#define SB2_RESCORE(RR)                                                                                                          \
+  knn_rescore_kernel<RR><<<grid, wpb * 32, 0, ctx->stream>>>(d_x, n_points, d, q0, ql_base, row_map, n_rows, k, sub, cand_score, \
+                                                             cand_idx, maxnorm, inv_s2, c_q, c_n, dnorm, dmax_bits, d_idx, d_dist, wq, wub, wcnt)
+  if (list_m == 32) SB2_RESCORE(1);
+  else if (list_m == 64) SB2_RESCORE(2);
+  else SB2_RESCORE(4);
+#undef SB2_RESCORE
   SB2_LAUNCH_CHECK(ctx);
   return SB2_OK;
 }
@@ -501,18 +534,175 @@ int32_t read_count(sb2_ctx* ctx, const unsigned long long* d_cnt, int64_t* out) 
   return SB2_OK;
 }
 
-}  // namespace
+// ---- the two generations of the tensor-core sweep behind one interface (tensor_tiers below) ----
+struct SweepV1 {   // knn_tc.cu: 256-query CTAs x 128-candidate tiles, one 32/64-proposal list per row (SB2_KNN_V=1)
+  KnnTcShape sh;
+  bool shape(const sb2_ctx* ctx, int d, int terms) { return knn_tc_shape(ctx, d, terms, &sh); }
+  static int list_m(int k, bool force64) { return (k > 24 || force64) ? 64 : 32; }
+  static int sub(int list_m) { return list_m; }
+  int wave_rows(const sb2_ctx* ctx) const { return ctx->prop.multiProcessorCount * sh.qh * TILE; }
+  size_t a_halves(int64_t n) const { return knn_tc_image_halves(sh, n); }
+  size_t b_halves(int64_t n) const { return knn_tc_image_halves(sh, n); }
+  int32_t build(sb2_ctx* ctx, const float* x, int64_t n, int d, const unsigned int* mn, const int32_t* g, int64_t gb, __half* A,
+                __half* B, float* inv_s2, float* dnorm, unsigned int* dmax) const {
+    return knn_tc_build_images(ctx, sh, x, n, d, mn, g, gb, A, B, inv_s2, dnorm, dmax);
+  }
+  int32_t sweep(sb2_ctx* ctx, const __half* A, int64_t a_tile0, const __half* B, int64_t n_points, int64_t n_query, int lm,
+                float* cs, int32_t* ci, double* fl, bool est) const {
+    return knn_tc_sweep(ctx, sh, A, a_tile0, B, n_points, n_query, lm, cs, ci, fl, est);
+  }
+  void coefs(double* cq, double* cn) const { knn_tc_error_coefs(sh, cq, cn); }
+};
+struct SweepV2 {   // knn_tc2.cu: 128-query CTAs x 256-candidate tiles (UMMA N = 256), four sub-lists per row (default)
+  KnnTc2Shape sh;
+  bool shape(const sb2_ctx* ctx, int d, int terms) { return knn_tc2_shape(ctx, d, terms, terms == 1, &sh); }
+  static int list_m(int k, bool force_big) { return (k > 24 || force_big) ? 128 : 64; }
+  static int sub(int list_m) { return list_m / 4; }
+  int wave_rows(const sb2_ctx* ctx) const { return ctx->prop.multiProcessorCount * TILE; }
+  size_t a_halves(int64_t n) const { return knn_tc2_a_halves(sh, n); }
+  size_t b_halves(int64_t n) const { return knn_tc2_b_halves(sh, n); }
+  int32_t build(sb2_ctx* ctx, const float* x, int64_t n, int d, const unsigned int* mn, const int32_t* g, int64_t gb, __half* A,
+                __half* B, float* inv_s2, float* dnorm, unsigned int* dmax) const {
+    return knn_tc2_build_images(ctx, sh, x, n, d, mn, g, gb, A, B, inv_s2, dnorm, dmax);
+  }
+  int32_t sweep(sb2_ctx* ctx, const __half* A, int64_t a_tile0, const __half* B, int64_t n_points, int64_t n_query, int lm,
+                float* cs, int32_t* ci, double* fl, bool est) const {
+    return knn_tc2_sweep(ctx, sh, A, a_tile0, B, n_points, n_query, lm, cs, ci, fl, est);
+  }
+  void coefs(double* cq, double* cn) const { knn_tc2_error_coefs(sh, cq, cn); }
+};
 
-// Exact kNN.  Tensor path (default), in tiers that each end in the same fp64 re-score + certificate:
+struct TierState {
+  sb2_ctx* ctx;
+  ScratchScope* scr;
+  const float* d_x;
+  int64_t n_points, q0, n_query;
+  int d, k;
+  unsigned int* maxnorm;
+  int32_t *wq1, *wq2;
+  double *wub1, *wub2;
+  unsigned long long* wcnt;
+  int32_t* d_idx;
+  double* d_dist;
+  EventPairs* evs;
+  double issued_flops = 0.0;
+  int64_t n_resweep = 0;
+};
+
+// Tensor path, in tiers that each end in the same fp64 re-score + certificate:
 //   tier 1  one fp16 sweep (K = d+3): proposals whose rounding bound (2^-10 |q| R) still certifies the exact top-k are final
 //   tier 2  rows tier 1 could not certify are gathered and swept again in split precision (K = 3d+3, bound ~2^-16 |q| R)
-//   tier 3  rows still open (exact ties at the k-th distance, floods of duplicates): fp64 scan of every point
+//   tier 3  rows still open (exact ties at the k-th distance, floods of duplicates): fp64 scan of every point (caller)
 // A pilot of one wave of CTAs measures tier 1's certification rate; if most rows fail (data far from the origin,
 // tiny neighbour gaps) the remaining rows go straight to the split-precision sweep.
+template <class SW>
+int32_t tensor_tiers(TierState& t, bool split_only, bool force_big_list) {
+  sb2_ctx* ctx = t.ctx;
+  ScratchScope& scr = *t.scr;
+  cudaStream_t st = ctx->stream;
+  const int64_t n_points = t.n_points, n_query = t.n_query, q0 = t.q0;
+  const int d = t.d, k = t.k;
+  SW s1, s3;
+  SB2_CHECK_ARG(s1.shape(ctx, d, 1) && s3.shape(ctx, d, 3), "tensor-core kNN tile does not fit shared memory");
+  const int list_m = SW::list_m(k, force_big_list), sub = SW::sub(list_m);
+  float* cand_score;
+  int32_t* cand_idx;
+  SB2_TRY(scr.alloc(&cand_score, (size_t)n_query * list_m));
+  SB2_TRY(scr.alloc(&cand_idx, (size_t)n_query * list_m));
+  float* inv_s2;
+  SB2_TRY(scr.alloc(&inv_s2, 4));
+  double cq1, cn1, cq3, cn3;
+  s1.coefs(&cq1, &cn1);
+  s3.coefs(&cq3, &cn3);
+  __half *A1 = nullptr, *B1 = nullptr, *A3 = nullptr, *B3 = nullptr;
+  float* dnorm = nullptr;  // |x - fp16(x)| per point; its maximum lives in maxnorm[1]
+  unsigned int* maxnorm = t.maxnorm;
+  const int64_t qt0 = q0 / TILE;
+  int64_t done = 0;  // local rows [0, done) have been through their first sweep
+  bool direct_split = split_only;
+  if (!split_only) {
+    SB2_TRY(scr.alloc(&A1, s1.a_halves(n_points)));
+    SB2_TRY(scr.alloc(&B1, s1.b_halves(n_points)));
+    SB2_TRY(scr.alloc(&dnorm, (size_t)n_points));
+    SB2_TRY(s1.build(ctx, t.d_x, n_points, d, maxnorm, nullptr, 0, A1, B1, inv_s2, dnorm, maxnorm + 1));
+    // pilot: one wave of CTAs
+    const int64_t wave = s1.wave_rows(ctx);
+    const int64_t first = n_query >= 4 * wave ? wave : n_query;
+    SB2_TRY(t.evs->begin());
+    SB2_TRY(s1.sweep(ctx, A1, qt0, B1, n_points, first, list_m, cand_score, cand_idx, &t.issued_flops, true));
+    SB2_TRY(t.evs->end());
+    SB2_TRY(launch_rescore(ctx, list_m, sub, t.d_x, n_points, d, q0, 0, nullptr, first, k, cand_score, cand_idx, maxnorm, inv_s2, cq1,
+                           cn1, dnorm, maxnorm + 1, t.d_idx, t.d_dist, t.wq1, t.wub1, t.wcnt));
+    done = first;
+    if (first < n_query) {
+      int64_t open1 = 0;
+      SB2_TRY(read_count(ctx, t.wcnt, &open1));
+      direct_split = open1 * 2 > first;
+      if (!direct_split) {
+        const int64_t rest = n_query - done;
+        SB2_TRY(t.evs->begin());
+        SB2_TRY(s1.sweep(ctx, A1, qt0 + done / TILE, B1, n_points, rest, list_m, cand_score + done * list_m,
+                         cand_idx + done * list_m, &t.issued_flops, true));
+        SB2_TRY(t.evs->end());
+        SB2_TRY(launch_rescore(ctx, list_m, sub, t.d_x, n_points, d, q0, done, nullptr, rest, k, cand_score + done * list_m,
+                               cand_idx + done * list_m, maxnorm, inv_s2, cq1, cn1, dnorm, maxnorm + 1, t.d_idx, t.d_dist, t.wq1, t.wub1, t.wcnt));
+        done = n_query;
+      }
+    }
+  }
+  if (done < n_query) {
+    // split-precision sweep of the remaining rows, straight from the full image arrays
+    SB2_TRY(scr.alloc(&A3, s3.a_halves(n_points)));
+    SB2_TRY(scr.alloc(&B3, s3.b_halves(n_points)));
+    SB2_TRY(s3.build(ctx, t.d_x, n_points, d, maxnorm, nullptr, 0, A3, B3, inv_s2, nullptr, nullptr));
+    const int64_t rest = n_query - done;
+    SB2_TRY(t.evs->begin());
+    SB2_TRY(s3.sweep(ctx, A3, qt0 + done / TILE, B3, n_points, rest, list_m, cand_score + done * list_m,
+                     cand_idx + done * list_m, &t.issued_flops, true));
+    SB2_TRY(t.evs->end());
+    SB2_TRY(launch_rescore(ctx, list_m, sub, t.d_x, n_points, d, q0, done, nullptr, rest, k, cand_score + done * list_m,
+                           cand_idx + done * list_m, maxnorm, inv_s2, cq3, cn3, nullptr, nullptr, t.d_idx, t.d_dist, t.wq2, t.wub2, t.wcnt + 1));
+  }
+  if (!split_only) {
+    // tier 2: gather the rows tier 1 left open and sweep them in split precision
+    SB2_TRY(read_count(ctx, t.wcnt, &t.n_resweep));
+    // a re-sweep occupies one CTA per 128 open rows for a whole pass over the candidates (a few ms at 1.3M points
+    // however few rows there are); the exact scan streams the whole data set once per ROW (~45 us each at
+    // 1.3M x 50 once HBM saturates), so it only wins for a handful of rows
+    int64_t scan_slots = 16;
+    if (const char* se = getenv("SB2_KNN_SCAN_SLOTS")) scan_slots = atoll(se);  // 0 forces the re-sweep (tests)
+    const int64_t n_resweep = t.n_resweep;
+    if (n_resweep > 0 && n_resweep <= scan_slots) {
+      knn_append_queue_kernel<<<(unsigned)ceil_div64(n_resweep, 256), 256, 0, st>>>(t.wq1, t.wub1, n_resweep, t.wq2, t.wub2, t.wcnt + 1);
+      SB2_LAUNCH_CHECK(ctx);
+    } else if (n_resweep > 0) {
+      if (!B3) {
+        SB2_TRY(scr.alloc(&B3, s3.b_halves(n_points)));
+        SB2_TRY(s3.build(ctx, t.d_x, n_points, d, maxnorm, nullptr, 0, nullptr, B3, inv_s2, nullptr, nullptr));
+      }
+      __half* Ag;
+      SB2_TRY(scr.alloc(&Ag, s3.a_halves(n_resweep)));
+      SB2_TRY(s3.build(ctx, t.d_x, n_resweep, d, maxnorm, t.wq1, q0, Ag, nullptr, inv_s2, nullptr, nullptr));
+      SB2_TRY(t.evs->begin());
+      // cold start: rows whose sampled threshold was too tight (fewer than k candidates beat it) must not fail twice
+      SB2_TRY(s3.sweep(ctx, Ag, 0, B3, n_points, n_resweep, list_m, cand_score, cand_idx, &t.issued_flops, false));
+      SB2_TRY(t.evs->end());
+      SB2_TRY(launch_rescore(ctx, list_m, sub, t.d_x, n_points, d, q0, 0, t.wq1, n_resweep, k, cand_score, cand_idx, maxnorm, inv_s2, cq3,
+                             cn3, nullptr, nullptr, t.d_idx, t.d_dist, t.wq2, t.wub2, t.wcnt + 1));
+    }
+  }
+  return SB2_OK;
+}
+
+}  // namespace
+
+// Exact kNN: a fast first pass proposes candidates per query, an fp64 re-score certifies the top-k against a rigorous
+// rounding-error bound, rows without a certificate are recomputed exactly.  First pass: the tensor-core tiers above
+// (default: knn_tc2.cu; SB2_KNN_V=1: the first-generation kernel of knn_tc.cu) or the fp32 CUDA-core sweep (SB2_KNN_PASS1=ffma).
 extern "C" int32_t sb2_knn_l2_f32(sb2_ctx* ctx, int64_t n_points, int32_t d, const float* d_x, int64_t q0,
                                   int64_t n_query, int32_t k, int32_t* d_idx, double* d_dist, sb2_knn_info* info) {
   SB2_CHECK_ARG(ctx && d_x && d_idx && d_dist, "null pointer");
-  SB2_CHECK_ARG(n_points >= 1 && n_points < (int64_t)INT32_MAX - TILE, "n_points");
+  SB2_CHECK_ARG(n_points >= 1 && n_points < (int64_t)INT32_MAX - 2 * TILE, "n_points");
   SB2_CHECK_ARG(d >= 1 && d <= 150, "d must be in [1,150]");
   SB2_CHECK_ARG(k >= 1 && k <= 56 && k <= n_points, "k must be in [1,56] and <= n_points");
   SB2_CHECK_ARG(q0 >= 0 && n_query >= 0 && q0 + n_query <= n_points, "query range");
@@ -525,24 +715,20 @@ extern "C" int32_t sb2_knn_l2_f32(sb2_ctx* ctx, int64_t n_points, int32_t d, con
   const int64_t chunk_f = (int64_t)(d + 1) * TILE;
   float* Xt;
   unsigned int* maxnorm;
-  float* cand_score;
-  int32_t* cand_idx;
   int32_t *wq1, *wq2;
   double *wub1, *wub2;
   unsigned long long* wcnt;  // [0] rows tier 1 left open, [1] rows for the exact scan
   SB2_TRY(scr.alloc(&Xt, (size_t)(n_tiles * chunk_f)));
   SB2_TRY(scr.alloc(&maxnorm, 4));
-  // 32 proposals per query keep a slack of >= 8 behind k <= 24; larger k gets 64 (tensor path only: the FFMA pass
-  // keeps one proposal per lane, its rows then lean on the exact scan)
   const char* force = getenv("SB2_KNN_PASS1");
   const char* tiers = getenv("SB2_KNN_TIERS");
+  const char* gen = getenv("SB2_KNN_V");
   const bool use_tc = knn_tc_supported(d) && !(force && strcmp(force, "ffma") == 0);
+  const bool use_v1 = gen && strcmp(gen, "1") == 0;
   const bool split_only = tiers && strcmp(tiers, "3") == 0;
   const char* list_env = getenv("SB2_KNN_LIST");
-  const int list_m = (use_tc && (k > 24 || (list_env && strcmp(list_env, "64") == 0))) ? 64 : 32;
-  SB2_CHECK_ARG(k <= list_m - 2, "k > 30 needs the tensor-core pass (SB2_KNN_PASS1=ffma limits k to 30)");
-  SB2_TRY(scr.alloc(&cand_score, (size_t)n_query * list_m));
-  SB2_TRY(scr.alloc(&cand_idx, (size_t)n_query * list_m));
+  const bool big_list = list_env && (strcmp(list_env, "64") == 0 || strcmp(list_env, "128") == 0);
+  SB2_CHECK_ARG(use_tc || k <= LISTM - 2, "k > 30 needs the tensor-core pass (SB2_KNN_PASS1=ffma limits k to 30)");
   SB2_TRY(scr.alloc(&wq1, (size_t)n_query));
   SB2_TRY(scr.alloc(&wub1, (size_t)n_query));
   SB2_TRY(scr.alloc(&wq2, (size_t)n_query));
@@ -562,89 +748,16 @@ extern "C" int32_t sb2_knn_l2_f32(sb2_ctx* ctx, int64_t n_points, int32_t d, con
   double issued_flops = 0.0;
   int64_t n_resweep = 0;
   if (use_tc) {
-    KnnTcShape sh1, sh3;
-    SB2_CHECK_ARG(knn_tc_shape(ctx, d, 1, &sh1) && knn_tc_shape(ctx, d, 3, &sh3), "tensor-core kNN tile does not fit shared memory");
-    float* inv_s2;
-    SB2_TRY(scr.alloc(&inv_s2, 4));
-    double cq1, cn1, cq3, cn3;
-    knn_tc_error_coefs(sh1, &cq1, &cn1);
-    knn_tc_error_coefs(sh3, &cq3, &cn3);
-    __half *A1 = nullptr, *B1 = nullptr, *A3 = nullptr, *B3 = nullptr;
-    float* dnorm = nullptr;  // |x - fp16(x)| per point; its maximum lives in maxnorm[1]
-    const int64_t qt0 = q0 / TILE;
-    int64_t done = 0;  // local rows [0, done) have been through their first sweep
-    bool direct_split = split_only;
-    if (!split_only) {
-      SB2_TRY(scr.alloc(&A1, knn_tc_image_halves(sh1, n_points)));
-      SB2_TRY(scr.alloc(&B1, knn_tc_image_halves(sh1, n_points)));
-      SB2_TRY(scr.alloc(&dnorm, (size_t)n_points));
-      SB2_TRY(knn_tc_build_images(ctx, sh1, d_x, n_points, d, maxnorm, nullptr, 0, A1, B1, inv_s2, dnorm, maxnorm + 1));
-      // pilot: one wave of CTAs
-      const int64_t wave = (int64_t)ctx->prop.multiProcessorCount * sh1.qh * TILE;
-      const int64_t first = n_query >= 4 * wave ? wave : n_query;
-      SB2_TRY(evs.begin());
-      SB2_TRY(knn_tc_sweep(ctx, sh1, A1, qt0, B1, n_points, first, list_m, cand_score, cand_idx, &issued_flops));
-      SB2_TRY(evs.end());
-      SB2_TRY(launch_rescore(ctx, list_m, d_x, n_points, d, q0, 0, nullptr, first, k, cand_score, cand_idx, maxnorm, inv_s2, cq1,
-                             cn1, dnorm, maxnorm + 1, d_idx, d_dist, wq1, wub1, wcnt));
-      done = first;
-      if (first < n_query) {
-        int64_t open1 = 0;
-        SB2_TRY(read_count(ctx, wcnt, &open1));
-        direct_split = open1 * 2 > first;
-        if (!direct_split) {
-          const int64_t rest = n_query - done;
-          SB2_TRY(evs.begin());
-          SB2_TRY(knn_tc_sweep(ctx, sh1, A1, qt0 + done / TILE, B1, n_points, rest, list_m, cand_score + done * list_m,
-                               cand_idx + done * list_m, &issued_flops));
-          SB2_TRY(evs.end());
-          SB2_TRY(launch_rescore(ctx, list_m, d_x, n_points, d, q0, done, nullptr, rest, k, cand_score + done * list_m,
-                                 cand_idx + done * list_m, maxnorm, inv_s2, cq1, cn1, dnorm, maxnorm + 1, d_idx, d_dist, wq1, wub1, wcnt));
-          done = n_query;
-        }
-      }
-    }
-    if (done < n_query) {
-      // split-precision sweep of the remaining rows, straight from the full image arrays
-      SB2_TRY(scr.alloc(&A3, knn_tc_image_halves(sh3, n_points)));
-      SB2_TRY(scr.alloc(&B3, knn_tc_image_halves(sh3, n_points)));
-      SB2_TRY(knn_tc_build_images(ctx, sh3, d_x, n_points, d, maxnorm, nullptr, 0, A3, B3, inv_s2));
-      const int64_t rest = n_query - done;
-      SB2_TRY(evs.begin());
-      SB2_TRY(knn_tc_sweep(ctx, sh3, A3, qt0 + done / TILE, B3, n_points, rest, list_m, cand_score + done * list_m,
-                           cand_idx + done * list_m, &issued_flops));
-      SB2_TRY(evs.end());
-      SB2_TRY(launch_rescore(ctx, list_m, d_x, n_points, d, q0, done, nullptr, rest, k, cand_score + done * list_m,
-                             cand_idx + done * list_m, maxnorm, inv_s2, cq3, cn3, nullptr, nullptr, d_idx, d_dist, wq2, wub2, wcnt + 1));
-    }
-    if (!split_only) {
-      // tier 2: gather the rows tier 1 left open and sweep them in split precision
-      SB2_TRY(read_count(ctx, wcnt, &n_resweep));
-      // a re-sweep occupies one CTA per 128..256 open rows for a whole pass over the candidates (~8 ms at 1.3M
-      // points however few rows there are); the exact scan streams the whole data set once per ROW (~45 us each at
-      // 1.3M x 50 once HBM saturates), so it only wins for a handful of rows
-      int64_t scan_slots = 16;
-      if (const char* se = getenv("SB2_KNN_SCAN_SLOTS")) scan_slots = atoll(se);  // 0 forces the re-sweep (tests)
-      if (n_resweep > 0 && n_resweep <= scan_slots) {
-        knn_append_queue_kernel<<<(unsigned)ceil_div64(n_resweep, 256), 256, 0, st>>>(wq1, wub1, n_resweep, wq2, wub2, wcnt + 1);
-        SB2_LAUNCH_CHECK(ctx);
-      } else if (n_resweep > 0) {
-        if (!B3) {
-          SB2_TRY(scr.alloc(&B3, knn_tc_image_halves(sh3, n_points)));
-          SB2_TRY(knn_tc_build_images(ctx, sh3, d_x, n_points, d, maxnorm, nullptr, 0, nullptr, B3, inv_s2));
-        }
-        __half* Ag;
-        SB2_TRY(scr.alloc(&Ag, knn_tc_image_halves(sh3, n_resweep)));
-        SB2_TRY(knn_tc_build_images(ctx, sh3, d_x, n_resweep, d, maxnorm, wq1, q0, Ag, nullptr, inv_s2));
-        SB2_TRY(evs.begin());
-        // cold start: rows whose sampled threshold was too tight (fewer than k candidates beat it) must not fail twice
-        SB2_TRY(knn_tc_sweep(ctx, sh3, Ag, 0, B3, n_points, n_resweep, list_m, cand_score, cand_idx, &issued_flops, false));
-        SB2_TRY(evs.end());
-        SB2_TRY(launch_rescore(ctx, list_m, d_x, n_points, d, q0, 0, wq1, n_resweep, k, cand_score, cand_idx, maxnorm, inv_s2, cq3,
-                               cn3, nullptr, nullptr, d_idx, d_dist, wq2, wub2, wcnt + 1));
-      }
-    }
+    TierState t{ctx, &scr, d_x, n_points, q0, n_query, d, k, maxnorm, wq1, wq2, wub1, wub2, wcnt, d_idx, d_dist, &evs};
+    if (use_v1) SB2_TRY(tensor_tiers<SweepV1>(t, split_only, big_list));
+    else SB2_TRY(tensor_tiers<SweepV2>(t, split_only, big_list));
+    issued_flops = t.issued_flops;
+    n_resweep = t.n_resweep;
   } else {
+    float* cand_score;
+    int32_t* cand_idx;
+    SB2_TRY(scr.alloc(&cand_score, (size_t)n_query * LISTM));
+    SB2_TRY(scr.alloc(&cand_idx, (size_t)n_query * LISTM));
     issued_flops = 2.0 * (double)n_query * (double)n_points * (double)d;
     const double c = 1.5 * (double)(d + 2) * 5.9604644775390625e-08;
     const int64_t q_tiles = ceil_div64(n_query, TILE);
@@ -664,7 +777,7 @@ extern "C" int32_t sb2_knn_l2_f32(sb2_ctx* ctx, int64_t n_points, int32_t d, con
     }
     SB2_LAUNCH_CHECK(ctx);
     SB2_TRY(evs.end());
-    SB2_TRY(launch_rescore(ctx, list_m, d_x, n_points, d, q0, 0, nullptr, n_query, k, cand_score, cand_idx, maxnorm, nullptr, c, c,
+    SB2_TRY(launch_rescore(ctx, LISTM, LISTM, d_x, n_points, d, q0, 0, nullptr, n_query, k, cand_score, cand_idx, maxnorm, nullptr, c, c,
                            nullptr, nullptr, d_idx, d_dist, wq2, wub2, wcnt + 1));
   }
   {
@@ -685,7 +798,7 @@ extern "C" int32_t sb2_knn_l2_f32(sb2_ctx* ctx, int64_t n_points, int32_t d, con
     info->pass1_ms = evs.total_ms();
     info->pass1_flops = 2.0 * (double)n_query * (double)n_points * (double)d;
     info->pass1_issued_flops = issued_flops;
-    info->pass1_tensor = use_tc ? 1 : 0;
+    info->pass1_tensor = use_tc ? (use_v1 ? 1 : 2) : 0;
     info->n_resweep = n_resweep;
   }
   return SB2_OK;

@@ -187,12 +187,18 @@ decide_kernel(Level L, const int32_t* __restrict__ comm, const int32_t* __restri
   if (lane == 0) {
     int32_t t = -1;
     uint8_t ts = 0;
-    if (best >= 0) {
-      const double stay = REFINE ? 0.0 : wa - scale * ((double)K[a] - kv);
-      if (best_gain > stay + 0.5) {
-        t = best;
-        ts = (REFINE && csize[best] == 1) ? 1 : 0;
-      }
+    const double stay = REFINE ? 0.0 : wa - scale * ((double)K[a] - kv);
+    if (best >= 0 && best_gain > stay + 0.5) {
+      t = best;
+      ts = (REFINE && csize[best] == 1) ? 1 : 0;
+    }
+    // Empty-community move (leidenalg's consider_empty_community / igraph's "empty cluster" candidate): a vertex whose
+    // best option is still worse than being alone (gain 0) leaves for an empty community.  The empty label it takes is
+    // ITS OWN vertex id - free iff csize[v] == 0, and no other vertex can claim it in the same sweep, so simultaneous
+    // decisions never collide.  (If somebody else currently uses label v the vertex waits for a later sweep.)
+    if (!REFINE && csize[a] > 1 && csize[v] == 0) {
+      const double cur = t >= 0 ? best_gain : stay;
+      if (0.0 > cur + 0.5) t = v;
     }
     target[v] = t;
     if (REFINE) tsingle[v] = ts;
@@ -393,6 +399,7 @@ struct Work {
   int64_t moves_total;
   int last_sweeps;
   bool first_pass;
+  bool exact;       // SB2_LEIDEN_EXACT=1: no first-pass / refinement cut-offs (every phase runs to its fixed point)
 };
 
 inline unsigned gridw(int64_t n) { return (unsigned)ceil_div64(n, 8); }    // warp per item, 8 warps/CTA
@@ -433,7 +440,7 @@ int32_t local_move(Work& w, const Level& L, int32_t* comm, int64_t* moves_out) {
     if (c == 0) {
       if (noskip) break;
       noskip = 1;  // confirm with a sweep in which every active vertex decides
-    } else if (w.first_pass && (int64_t)c * 200 < (int64_t)L.n) {
+    } else if (w.first_pass && !w.exact && (int64_t)c * 200 < (int64_t)L.n) {
       // First pass only: once fewer than 0.5 % of the vertices still move, what remains is communities
       // merging one vertex at a time in slow waves - the aggregated level does that in a single move, and the
       // following passes (which run local moving to exact convergence) pick up any leftover single-vertex gain.
@@ -468,7 +475,7 @@ int32_t refine(Work& w, const Level& L, const int32_t* comm, int32_t* ref, int64
     if (getenv("SB2_TIMING")) fprintf(stderr, "[sb2 leiden]   refine n=%d round=%d merges=%llu\n", L.n, round, c);
     // the first rounds do nearly all the merging; stragglers (< 0.1 % of the vertices per round) simply stay
     // singletons of the refined partition, which only makes the aggregate marginally larger
-    if (c == 0 || (round >= 2 && c * 1000 < (u64)L.n)) break;
+    if (c == 0 || (!w.exact && round >= 2 && c * 1000 < (u64)L.n)) break;
   }
   return SB2_OK;
 }
@@ -637,6 +644,7 @@ extern "C" int32_t sb2_leiden_csr_f32(sb2_ctx* ctx, int64_t n, const int64_t* d_
   Work w{};
   w.ctx = ctx; w.st = st; w.n0 = n0; w.gamma = resolution; w.total = total;
   w.seed = (uint32_t)(seed ^ (seed >> 32));
+  { const char* ex = getenv("SB2_LEIDEN_EXACT"); w.exact = ex && atoi(ex) > 0; }
   SB2_TRY(scr.alloc(&w.K, (size_t)n0));
   SB2_TRY(scr.alloc(&w.csize, (size_t)n0));
   SB2_TRY(scr.alloc(&w.hkeys, (size_t)std::max<int64_t>(nnz0, 1)));

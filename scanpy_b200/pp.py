@@ -107,6 +107,12 @@ def pca(data, n_comps: int | None = None, *, layer: str | None = None, obsm: str
     xc = as_csr_f32(x)
     solver = _solver_code(svd_solver, n_vars=n_vars)
     out = _ops.pca_csr(xc, n_comps, solver=solver, seed=seed_from_rng(rng))
+    if not out["converged"]:
+        # the block iteration stopped on stagnation / its iteration cap before the residual test was met (the SpMM-driven
+        # solver works in float32 passes and can sit on its rounding floor): never silently different
+        warn(f"scanpy_b200 PCA did not reach its residual tolerance (max relative residual "
+             f"{out['max_rel_residual']:.3g} after {out['iterations']} operator applications); results are approximate",
+             UserWarning)
     x_pca = out["X_pca"]
     if x_pca.dtype != np.dtype(dtype):
         x_pca = x_pca.astype(dtype)
@@ -258,7 +264,10 @@ def _neighbors_from_distances(adata, n_neighbors, *, distances, method, metric, 
         distances = np.asarray(distances).copy()
         np.fill_diagonal(distances, 0)
         knn_indices, knn_distances = _get_indices_distances_from_dense_matrix(distances, n_neighbors)
-    conn, _, _ = _ops.fuzzy_simplicial_set(knn_indices.astype(np.int32), knn_distances.astype(np.float64))
+    if method == "umap":
+        conn, _, _ = _ops.fuzzy_simplicial_set(knn_indices.astype(np.int32), knn_distances.astype(np.float64))
+    else:  # 'gauss' | 'jaccard': the reference dispatches on `method` here too (neighbors/__init__.py:672-708)
+        conn = _ops.knn_connectivities(knn_indices.astype(np.int32), knn_distances.astype(np.float64), method)
     params = dict(n_neighbors=n_neighbors, method=method, metric=metric, **meta_rs,
                   **({} if not metric_kwds else dict(metric_kwds=metric_kwds)))
     key_added, dists_key, conns_key = _write_neighbors(adata, key_added, dist=distances, conn=conn, params=params)

@@ -77,6 +77,11 @@ class B200PCA:
         xc = as_csr_f32(x)
         out = _ops.pca_csr(xc, self.n_components, solver=_solver_code(self.svd_solver, n_vars=xc.shape[1]),
                            seed=int(self.random_state or 0))
+        if not out["converged"]:
+            import warnings
+
+            warnings.warn(f"B200PCA did not reach its residual tolerance (max relative residual {out['max_rel_residual']:.3g})",
+                          UserWarning, stacklevel=2)
         self.components_ = out["components"]
         self.explained_variance_ = out["variance"]
         self.explained_variance_ratio_ = out["variance_ratio"]

@@ -301,13 +301,85 @@ def test_leiden_properties_and_quality(pbmc68k_graph):
     assert abs(_ops.modularity(g, m0) - q0) < 1e-12
     mo, qo, _ = old.leiden(g, seed=0)
     assert q0 >= qo - 1e-3                                 # quality guard vs the sequential oracle
-    assert adjusted_rand_score(mo, m0) > 0.9               # reference's own flavour-vs-flavour bar is NMI > 0.9
-    assert adjusted_rand_score(m1, m0) > 0.9
+    assert adjusted_rand_score(m1, m0) > 0.9               # other seed: same structure (label-level gate: next test)
     lo, _, _ = _ops.leiden(g, resolution=0.2, seed=0)
     hi, _, _ = _ops.leiden(g, resolution=3.0, seed=0)
     assert lo.max() < m0.max() < hi.max()
     two, _, i2 = _ops.leiden(g, n_iterations=2, seed=0)
     assert i2["passes"] == 2
+
+
+def _overlapping_knn_graph(n, k=15, seed=0, sep=1.6):
+    """UMAP connectivities of overlapping gaussian clusters (NOT separable blobs) through the CUDA kNN + fuzzy set."""
+    rs = np.random.RandomState(seed)
+    centers = rs.standard_normal((12, 10)) * sep
+    lab = rs.randint(0, 12, n)
+    x = (centers[lab] + rs.standard_normal((n, 10))).astype(np.float32)
+    idx, dist, _ = _ops.knn(x, k)
+    c, _, _ = _ops.fuzzy_simplicial_set(idx, dist)
+    return c, lab
+
+
+def test_leiden_real_graph_within_oracle_spread(pbmc68k_graph):
+    """Label-level gate on the reference's own real-data graph.  ARI >= 0.99 against ONE oracle run is not a property
+    the sequential algorithm itself has there (tests/test_oracle_leiden_guarantees.py: seed-to-seed ARI 0.95-1.0, for
+    both back-end flavours), so the gate is: for >= 5 seeds, quality at least the oracle's median and agreement with the
+    oracle runs no worse than the oracle runs agree among themselves; plus the reference's own NMI > 0.9 bar
+    (tests/test_clustering.py:130-163)."""
+    from sklearn.metrics import normalized_mutual_info_score
+
+    f = pbmc68k_graph
+    g = sparse.csr_matrix((f["conn_data"].astype(np.float32), f["conn_indices"], f["conn_indptr"]), shape=(700, 700))
+    oracle = [old.leiden(g, seed=s, beta=b) for b in (0.0, 0.01) for s in range(6)]       # both flavours
+    o_ari = [adjusted_rand_score(oracle[i][0], oracle[j][0]) for i in range(len(oracle)) for j in range(i)]
+    q_med = float(np.median([r[1] for r in oracle]))
+    worst = []
+    for seed in range(6):
+        m, q, _ = _ops.leiden(g, seed=seed)
+        a = [adjusted_rand_score(r[0], m) for r in oracle]
+        nmi = [normalized_mutual_info_score(r[0], m) for r in oracle]
+        worst.append(min(a))
+        assert q >= q_med - 1e-3, (seed, q, q_med)                       # quality: not below the oracle's median
+        assert np.median(a) >= np.median(o_ari) - 0.02, (seed, np.median(a), np.median(o_ari))
+        assert min(a) >= min(o_ari) - 0.02, (seed, min(a), min(o_ari))   # inside the oracle's own spread
+        assert min(nmi) > 0.9
+        assert m.max() == oracle[0][0].max()                             # same number of communities (12)
+    print(f"\n[pbmc68k] oracle-vs-oracle ARI min {min(o_ari):.3f} median {np.median(o_ari):.3f}; CUDA-vs-oracle worst {min(worst):.3f}")
+
+
+def test_leiden_cutoffs_and_empty_moves_do_not_cost_quality(monkeypatch):
+    """The two performance cut-offs (first-pass local moving stops below 0.5 % movers, refinement stops below 0.1 %
+    merges) against SB2_LEIDEN_EXACT=1, which runs every phase to its fixed point - on overlapping clusters."""
+    g, lab = _overlapping_knn_graph(60_000)
+    m_fast, q_fast, _ = _ops.leiden(g, seed=0)
+    monkeypatch.setenv("SB2_LEIDEN_EXACT", "1")
+    m_exact, q_exact, _ = _ops.leiden(g, seed=0)
+    monkeypatch.delenv("SB2_LEIDEN_EXACT")
+    mo, qo, _ = old.leiden(g, seed=0)
+    mo2, qo2, _ = old.leiden(g, seed=1)
+    spread = adjusted_rand_score(mo, mo2)
+    print(f"\n[overlap 60k] Q cut-offs {q_fast:.5f} exact {q_exact:.5f} oracle {qo:.5f}/{qo2:.5f}; ARI fast-vs-exact "
+          f"{adjusted_rand_score(m_fast, m_exact):.3f}, fast-vs-oracle {adjusted_rand_score(m_fast, mo):.3f}, oracle seed-vs-seed {spread:.3f}")
+    assert q_fast >= q_exact - 1e-3 and q_fast >= min(qo, qo2) - 1e-3
+    assert adjusted_rand_score(m_fast, mo) >= spread - 0.03
+    assert adjusted_rand_score(m_exact, mo) >= spread - 0.03
+
+
+def test_leiden_overlapping_100k_vs_oracle():
+    g, lab = _overlapping_knn_graph(100_000, sep=1.3)
+    m, q, info = _ops.leiden(g, seed=0)
+    runs = [old.leiden(g, seed=s) for s in range(3)]
+    o_ari = [adjusted_rand_score(runs[i][0], runs[j][0]) for i in range(3) for j in range(i)]
+    a = [adjusted_rand_score(r[0], m) for r in runs]
+    print(f"\n[overlap 100k] Q {q:.5f} oracle {[round(r[1], 5) for r in runs]}; ARI vs oracle {np.round(a, 3)}, oracle seed-vs-seed {np.round(o_ari, 3)}; "
+          f"ARI vs planted {adjusted_rand_score(lab, m):.3f} (oracle {adjusted_rand_score(lab, runs[0][0]):.3f})")
+    assert q >= min(r[1] for r in runs) - 1e-3
+    assert min(a) >= min(o_ari) - 0.03
+    # every community connected (the Leiden guarantee), checked on the CUDA result
+    from scipy.sparse.csgraph import connected_components
+    for c in range(m.max() + 1):
+        mem = np.flatnonzero(m == c)
+        assert connected_components(g[mem][:, mem], directed=False)[0] == 1
 
 
 def test_leiden_planted_ari(synth_small):
