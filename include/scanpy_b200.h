@@ -71,7 +71,8 @@ typedef struct sb2_knn_info {
   float pass1_ms;           /* CUDA-event duration of all first-pass sweep launches on the ctx stream */
   double pass1_flops;       /* 2 * n_query * n_points * d: the algorithmic flops of that launch */
   double pass1_issued_flops; /* flops actually issued (tensor path: padded tiles x split-precision K axis) */
-  int32_t pass1_tensor;     /* 1 = knn_pass1_tc_kernel (tcgen05), 0 = knn_pass1_kernel (fp32 FFMA) */
+  int32_t pass1_tensor;     /* 2 = knn_sweep2_kernel (tcgen05 N=256, default), 1 = knn_pass1_tc_kernel (first-generation tcgen05
+                               sweep: SB2_KNN_V=1 or K axes too wide for generation 2), 0 = knn_pass1_kernel (fp32 FFMA) */
   int64_t n_resweep;        /* rows the fp16 tier left uncertified, swept again in split precision (tensor path) */
 } sb2_knn_info;
 
@@ -133,14 +134,22 @@ int32_t sb2_csr_gram(sb2_ctx* ctx, int64_t n, int32_t g, const int64_t* d_indptr
  * array (q0 % 128 == 0 unless n_query == n_points).  k includes the query itself: column 0 of
  * the outputs is the query row with distance 0 (src/scanpy/neighbors/_common.py:74-98).
  * Outputs [n_query x k]: d_idx int32 (global row ids), d_dist float64, ascending by (distance, id).
- * k <= 56 (k <= 30 when d > 52).  Exactness: a fast first pass (tcgen05 split-fp16 for d <= 52, fp32 FFMA otherwise)
- * proposes 32 (k <= 24) or 64 candidates per query, an fp64 re-score certifies the top-k against a rounding-error
- * bound, uncertified rows are recomputed exactly. */
+ * d <= 150, k <= 56.  Exactness: a fast first pass (tcgen05 fp16 / split-fp16 sweeps; SB2_KNN_PASS1=ffma selects the
+ * fp32 CUDA-core sweep, k <= 30) proposes 32 (k <= 24) or 64 candidates per query, an fp64 re-score certifies the top-k
+ * against a rounding-error bound, uncertified rows are recomputed exactly. */
 int32_t sb2_knn_l2_f32(sb2_ctx* ctx, int64_t n_points, int32_t d, const float* d_x, int64_t q0, int64_t n_query,
                        int32_t k, int32_t* d_idx, double* d_dist, sb2_knn_info* info);
 
+/* test / debug entry: raw proposals (scores in the sweep's scaled units + ids, 64 per point) of ONE cold-start tensor-core
+ * sweep in the operand format `terms` (1: fp16, 3: split fp16) and the quantities its rounding-error certificate uses:
+ * h_meta[6] = { inv_s2 (score_true = score * inv_s2), largest squared norm R^2, max_p |x_p - fp16(x_p)|, c_q, c_n, list_m };
+ * the certificate bounds |score * inv_s2 - (q.c - |c|^2/2)| by  c_n R^2/2 + c_q |q| R  (+ for terms = 1:
+ * dnorm[q] R + (|q| + dnorm[q]) max dnorm).  d_dnorm [n_points] may be NULL. */
+int32_t sb2_knn_debug_proposals_f32(sb2_ctx* ctx, int64_t n_points, int32_t d, const float* d_x, int32_t terms,
+                                    float* d_score, int32_t* d_idx, float* d_dnorm, double* h_meta);
+
 /* ---- UMAP fuzzy simplicial set -> symmetric connectivities CSR -------------------------------
- * d_knn_idx/d_knn_dist [n x k] (column 0 = self), as produced by sb2_knn_l2_f32.
+ * d_knn_idx/d_knn_dist [n x k] (column 0 = self), as produced by sb2_knn_l2_f32; 2 <= k <= 64.
  * Output CSR: d_indptr int64[n+1], d_indices int32[cap], d_data float32[cap]; cap >= 2*n*(k-1) is
  * always enough.  Rows sorted by column, no explicit zeros, zero diagonal. */
 int32_t sb2_fuzzy_simplicial_set_f32(sb2_ctx* ctx, int64_t n, int32_t k, const int32_t* d_knn_idx,

@@ -24,7 +24,7 @@
 
 namespace {
 
-constexpr int MAXK = 32;
+constexpr int MAXK = 64;   // k-lists up to 64 entries (the kNN kernel serves k <= 56); kernels are instantiated for 32 and 64
 
 __global__ void sum_f32cast_kernel(const double* __restrict__ x, int64_t n, double* __restrict__ out) {
   double s = 0.0;
@@ -34,16 +34,17 @@ __global__ void sum_f32cast_kernel(const double* __restrict__ x, int64_t n, doub
   if ((threadIdx.x & 31) == 0) atomicAdd(out, s);
 }
 
+template <int MK>   // MK >= k: length of the thread's register-resident k-list
 __global__ void __launch_bounds__(128)
 fuzzy_rows_kernel(int64_t n, int k, const int32_t* __restrict__ knn_idx, const double* __restrict__ knn_dist,
                   float local_connectivity, const double* __restrict__ dist_sum, float* __restrict__ w_out,
                   float* __restrict__ sigmas, float* __restrict__ rhos) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  float d[MAXK];
+  float d[MK];
   double row_sum = 0.0;
 #pragma unroll
-  for (int j = 0; j < MAXK; ++j) {
+  for (int j = 0; j < MK; ++j) {
     d[j] = j < k ? (float)knn_dist[i * k + j] : 0.0f;
     if (j < k) row_sum += (double)d[j];
   }
@@ -53,7 +54,7 @@ fuzzy_rows_kernel(int64_t n, int k, const int32_t* __restrict__ knn_idx, const d
   int nnz = 0;
   float nz_im1 = 0.0f, nz_i = 0.0f, nz_0 = 0.0f, nz_max = 0.0f;
 #pragma unroll
-  for (int j = 0; j < MAXK; ++j) {
+  for (int j = 0; j < MK; ++j) {
     if (j < k && d[j] > 0.0f) {
       if (nnz == 0) nz_0 = d[j];
       if (nnz == index - 1) nz_im1 = d[j];
@@ -79,7 +80,7 @@ fuzzy_rows_kernel(int64_t n, int k, const int32_t* __restrict__ knn_idx, const d
   for (int it = 0; it < 64; ++it) {
     double psum = 0.0;
 #pragma unroll
-    for (int j = 1; j < MAXK; ++j) {
+    for (int j = 1; j < MK; ++j) {
       if (j < k) {
         const float dd = d[j] - rho;
         psum += dd > 0.0f ? exp(-((double)dd / mid)) : 1.0;
@@ -106,7 +107,7 @@ fuzzy_rows_kernel(int64_t n, int k, const int32_t* __restrict__ knn_idx, const d
   rhos[i] = rho;
   // membership strengths (compute_membership_strengths), float32
 #pragma unroll
-  for (int j = 0; j < MAXK; ++j) {
+  for (int j = 0; j < MK; ++j) {
     if (j < k) {
       const int32_t nb = knn_idx[i * k + j];
       float val;
@@ -241,10 +242,11 @@ __global__ void jaccard_rows_kernel(int64_t n, int k, const int32_t* __restrict_
   w[t] = val;
 }
 // gauss, sparse kNN branch (:17-100): sigma_i^2 = median of the k-1 squared neighbour distances
+template <int MK>
 __global__ void gauss_sigma_kernel(int64_t n, int k, const double* __restrict__ knn_dist, double* __restrict__ sig_sq) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  double d[MAXK];
+  double d[MK];
   const int m = k - 1;
   for (int j = 0; j < m; ++j) { const double x = knn_dist[i * k + 1 + j]; d[j] = x * x; }
   for (int a = 1; a < m; ++a) {  // insertion sort (rows arrive ascending already)
@@ -315,7 +317,7 @@ extern "C" int32_t sb2_knn_connectivities_f64(sb2_ctx* ctx, int64_t n, int32_t k
                                               const double* d_knn_dist, int32_t method, int64_t* d_indptr,
                                               int32_t* d_indices, double* d_data, int64_t cap, int64_t* h_nnz) {
   SB2_CHECK_ARG(ctx && d_knn_idx && d_indptr && d_indices && d_data && h_nnz, "null pointer");
-  SB2_CHECK_ARG(n >= 1 && k >= 2 && k <= MAXK, "k must be in [2,32]");
+  SB2_CHECK_ARG(n >= 1 && k >= 2 && k <= MAXK, "k must be in [2,64]");
   SB2_CHECK_ARG(method == 1 || method == 2, "method: 1 = gauss, 2 = jaccard");
   SB2_CHECK_ARG(method == 2 || d_knn_dist, "gauss needs distances");
   SB2_CUDA(cudaSetDevice(ctx->device));
@@ -331,7 +333,8 @@ extern "C" int32_t sb2_knn_connectivities_f64(sb2_ctx* ctx, int64_t n, int32_t k
   }
   double* sig_sq;
   SB2_TRY(scr.alloc(&sig_sq, (size_t)n));
-  gauss_sigma_kernel<<<(unsigned)ceil_div64(n, 128), 128, 0, st>>>(n, k, d_knn_dist, sig_sq);
+  if (k <= 32) gauss_sigma_kernel<32><<<(unsigned)ceil_div64(n, 128), 128, 0, st>>>(n, k, d_knn_dist, sig_sq);
+  else gauss_sigma_kernel<64><<<(unsigned)ceil_div64(n, 128), 128, 0, st>>>(n, k, d_knn_dist, sig_sq);
   SB2_LAUNCH_CHECK(ctx);
   gauss_rows_kernel<<<(unsigned)ceil_div64(nk, 256), 256, 0, st>>>(n, k, d_knn_idx, d_knn_dist, sig_sq, w);
   SB2_LAUNCH_CHECK(ctx);
@@ -344,7 +347,7 @@ extern "C" int32_t sb2_fuzzy_simplicial_set_f32(sb2_ctx* ctx, int64_t n, int32_t
                                                 float* d_data, int64_t cap, int64_t* h_nnz, float* d_sigmas,
                                                 float* d_rhos) {
   SB2_CHECK_ARG(ctx && d_knn_idx && d_knn_dist && d_indptr && d_indices && d_data && h_nnz, "null pointer");
-  SB2_CHECK_ARG(n >= 1 && k >= 2 && k <= MAXK, "k must be in [2,32]");
+  SB2_CHECK_ARG(n >= 1 && k >= 2 && k <= MAXK, "k must be in [2,64]");
   SB2_CHECK_ARG(set_op_mix_ratio >= 0.0f && set_op_mix_ratio <= 1.0f, "set_op_mix_ratio in [0,1]");
   SB2_CHECK_ARG(local_connectivity >= 0.0f && local_connectivity < (float)k, "local_connectivity");
   SB2_CUDA(cudaSetDevice(ctx->device));
@@ -360,8 +363,12 @@ extern "C" int32_t sb2_fuzzy_simplicial_set_f32(sb2_ctx* ctx, int64_t n, int32_t
   SB2_CUDA(cudaMemsetAsync(dsum, 0, 16, st));
   sum_f32cast_kernel<<<ctx->prop.multiProcessorCount * 4, 256, 0, st>>>(d_knn_dist, nk, dsum);
   SB2_LAUNCH_CHECK(ctx);
-  fuzzy_rows_kernel<<<(unsigned)ceil_div64(n, 128), 128, 0, st>>>(n, k, d_knn_idx, d_knn_dist, local_connectivity, dsum, w,
-                                                                 d_sigmas ? d_sigmas : sig, d_rhos ? d_rhos : rho);
+  if (k <= 32)
+    fuzzy_rows_kernel<32><<<(unsigned)ceil_div64(n, 128), 128, 0, st>>>(n, k, d_knn_idx, d_knn_dist, local_connectivity, dsum, w,
+                                                                        d_sigmas ? d_sigmas : sig, d_rhos ? d_rhos : rho);
+  else
+    fuzzy_rows_kernel<64><<<(unsigned)ceil_div64(n, 128), 128, 0, st>>>(n, k, d_knn_idx, d_knn_dist, local_connectivity, dsum, w,
+                                                                        d_sigmas ? d_sigmas : sig, d_rhos ? d_rhos : rho);
   SB2_LAUNCH_CHECK(ctx);
   return symmetrize<float>(ctx, scr, n, k, d_knn_idx, w, SYM_FUZZY_UNION, set_op_mix_ratio, d_indptr, d_indices, d_data, cap,
                            h_nnz);

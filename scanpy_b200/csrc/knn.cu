@@ -803,3 +803,57 @@ extern "C" int32_t sb2_knn_l2_f32(sb2_ctx* ctx, int64_t n_points, int32_t d, con
   }
   return SB2_OK;
 }
+
+// Debug / test entry: the raw proposals of ONE cold-start tensor sweep (generation 2) in the chosen operand format, with
+// everything the rounding-error certificate is computed from, so that a test can MEASURE |s_tensor - s_exact| on the
+// hardware against the bound knn_rescore_kernel uses (tests/test_gpu_parity.py::test_knn_tensor_score_error_within_bound).
+//   d_score / d_idx [n_points x list_m]: proposal scores in the kernel's scaled units and their point ids (-1: unused)
+//   d_dnorm [n_points]: |x - fp16(x)| per point (terms = 1 only, else untouched)
+//   h_meta[6] = { inv_s2 (score_true = score * inv_s2), R^2 (largest squared norm), max_p dnorm[p], c_q, c_n, list_m }
+extern "C" int32_t sb2_knn_debug_proposals_f32(sb2_ctx* ctx, int64_t n_points, int32_t d, const float* d_x, int32_t terms,
+                                               float* d_score, int32_t* d_idx, float* d_dnorm, double* h_meta) {
+  SB2_CHECK_ARG(ctx && d_x && d_score && d_idx && h_meta, "null pointer");
+  SB2_CHECK_ARG(terms == 1 || terms == 3, "terms must be 1 (fp16) or 3 (split fp16)");
+  SB2_CHECK_ARG(n_points >= 1 && d >= 1 && d <= 150, "n_points / d");
+  SB2_CUDA(cudaSetDevice(ctx->device));
+  cudaStream_t st = ctx->stream;
+  ScratchScope scr(ctx);
+  const int64_t n_tiles = ceil_div64(n_points, TILE);
+  float* Xt;
+  unsigned int* maxnorm;
+  float* inv_s2;
+  SB2_TRY(scr.alloc(&Xt, (size_t)(n_tiles * (d + 1) * TILE)));
+  SB2_TRY(scr.alloc(&maxnorm, 4));
+  SB2_TRY(scr.alloc(&inv_s2, 4));
+  SB2_CUDA(cudaMemsetAsync(maxnorm, 0, 16, st));
+  {
+    size_t smem = (size_t)TILE * d * sizeof(float);
+    SB2_CUDA(cudaFuncSetAttribute(knn_prep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    knn_prep_kernel<<<(unsigned)n_tiles, 256, smem, st>>>(d_x, n_points, d, Xt, maxnorm);
+    SB2_LAUNCH_CHECK(ctx);
+  }
+  KnnTc2Shape sh;
+  SB2_CHECK_ARG(knn_tc2_shape(ctx, d, terms, false, &sh), "tile does not fit shared memory");
+  __half *A, *B;
+  SB2_TRY(scr.alloc(&A, knn_tc2_a_halves(sh, n_points)));
+  SB2_TRY(scr.alloc(&B, knn_tc2_b_halves(sh, n_points)));
+  float* dn = d_dnorm;
+  if (!dn) SB2_TRY(scr.alloc(&dn, (size_t)n_points));
+  SB2_TRY(knn_tc2_build_images(ctx, sh, d_x, n_points, d, maxnorm, nullptr, 0, A, B, inv_s2, terms == 1 ? dn : nullptr,
+                               terms == 1 ? maxnorm + 1 : nullptr));
+  const int list_m = 64;
+  double fl = 0.0;
+  SB2_TRY(knn_tc2_sweep(ctx, sh, A, 0, B, n_points, n_points, list_m, d_score, d_idx, &fl, false));
+  float h_inv = 0.0f;
+  unsigned int h_bits[2] = {0, 0};
+  SB2_CUDA(cudaMemcpyAsync(&h_inv, inv_s2, 4, cudaMemcpyDeviceToHost, st));
+  SB2_CUDA(cudaMemcpyAsync(h_bits, maxnorm, 8, cudaMemcpyDeviceToHost, st));
+  SB2_CUDA(cudaStreamSynchronize(st));
+  float r2, dmax;
+  memcpy(&r2, &h_bits[0], 4);
+  memcpy(&dmax, &h_bits[1], 4);
+  double cq, cn;
+  knn_tc2_error_coefs(sh, &cq, &cn);
+  h_meta[0] = h_inv; h_meta[1] = r2; h_meta[2] = terms == 1 ? dmax : 0.0; h_meta[3] = cq; h_meta[4] = cn; h_meta[5] = list_m;
+  return SB2_OK;
+}

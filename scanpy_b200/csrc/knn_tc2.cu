@@ -5,30 +5,41 @@
 // is largest, plus a rigorous bound on the rounding error of s, so that knn_rescore_kernel can certify the exact fp64
 // top-k.  Operand formats (terms = 1: fp16, K = d+3; terms = 3: split fp16, K = 3d+3) are unchanged.
 //
-// What round 2 measured on the first generation (profiles/README.md, scripts/ubench/mma_smem_contention.cu):
+// What round 2 measured on the first generation (profiles/README.md, scripts/ubench/mma_smem_contention.cu,
+// alu_max_rate.cu, the SB2_KNN_DBG / SB2_KNN2_NOSCAN cycle stamps):
 //   * a 128x128x16 tcgen05.mma with both operands in shared memory reads 8 KB per 64 tensor cycles = 128 B/clk, ALL of
-//     the shared-memory bandwidth; with the bulk-copy ring writing candidate images next to it the pipe delivered one
-//     MMA per ~105 cycles (the sweep ran at 850 cycles per 256x128 tile even with an empty epilogue, 512 ideal);
-//     128x256x16 MMAs (12 KB per 128 cycles) kept 131-138 cycles per MMA under the same traffic;
-//   * the epilogue (two warps per scheduler, one long dependent max-tree each) needed ~1200 cycles per tile: too little
-//     instruction-level parallelism, and the accumulator hand-off (fill -> drain -> fill) was serial with it.
-// Hence this shape:
-//   CTA = 128 queries (UMMA M) x all candidate tiles of 256 points (UMMA N = 256), two 256-column accumulator
-//   buffers in TMEM, 18 warps:
-//     warp 0      producer: 1-D cp.async.bulk of pre-arranged candidate images (or K-slices of them) into an
-//                 mbarrier ring that takes all the shared memory left
-//     warp 1      MMA issuer (whole-warp loop, elect.sync inside the asm block, operands on the uniform datapath);
+//     the shared-memory bandwidth; next to the bulk-copy ring the pipe delivered one MMA per ~105 cycles (850 cycles per
+//     256x128 tile even with an EMPTY epilogue, 512 ideal).  128x256x16 MMAs (12 KB per 128 cycles) hold 131-138 cycles
+//     under the same traffic: with N = 256 and scanners that only load and release, this kernel runs at 521-546 cycles
+//     per 128x256 tile (tensor floor 512; power-capped at ~1000 W: 1450-1630 TFLOP/s issued);
+//   * the first generation's epilogue (two warps per scheduler, one dependent max tree each) had too little instruction
+//     level parallelism: ~1200 cycles per tile.
+// Hence this shape (one CTA per SM, 18 warps):
+//   CTA = 128 queries (UMMA M) x all candidate tiles of 256 points (UMMA N = 256), two 256-column accumulator buffers.
+//     warps 0-15  epilogue, FOUR warps per TMEM lane quadrant: warp (quadrant q, column quarter cq) owns rows
+//                 32q..32q+31 x columns 64cq..64cq+63 of every tile: tcgen05.ld.32x32b.x32 of its first chunk, examine,
+//                 load the second, release the buffer (16th arrival), examine.  Each (row, column quarter) keeps its
+//                 OWN register-resident proposal sub-list (16 or 32 scores in groups of 8 with group minima; ids
+//                 write-only to global memory): no cross-warp traffic in the loop.  A point outside all four sub-lists
+//                 of a row scored at most max(tau_0..tau_3), which is what the re-score certificate uses.
+//     warp 16     producer: 1-D cp.async.bulk of pre-arranged candidate images (or K-slices of them) into an mbarrier
+//                 ring that takes all the shared memory left
+//     warp 17     MMA issuer (whole-warp loop, elect.sync inside the asm block, operands on the uniform datapath);
 //                 tcgen05.commit frees the ring stage and publishes the accumulator buffer; owns TMEM alloc/dealloc
-//     warps 2-17  epilogue, FOUR warps per TMEM lane quadrant: warp (quadrant q, column quarter cq) owns rows
-//                 32q..32q+31 x columns 64cq..64cq+63 of every tile: one round trip of two tcgen05.ld.32x32b.x32, the
-//                 buffer is released as soon as the values are in registers (drain = one TMEM load latency), then the
-//                 two chunks are examined.  Each (row, column quarter) keeps its OWN register-resident proposal
-//                 sub-list (16 or 32 scores in groups of 8 with group minima; ids write-only to global memory): no
-//                 cross-warp traffic in the loop.  A point outside all four sub-lists of a row scored at most
-//                 max(tau_0..tau_3), which is what the re-score certificate uses.
+//   Service warps carry the highest warp ids (the sub-partition arbiter prefers them among eligible warps).
 //   Starting threshold: the first n/16 visits sweep every 16th tile and keep the 6 largest chunk maxima per (row,
 //   quarter); the four quarters of a row are merged through shared memory once (named barrier over the 16 epilogue
 //   warps) and the 6th largest of the 24 seeds all four sub-lists (rank ~96 of the row, as before).
+//   Sweep front: CTAs walk the candidate tiles cyclically, starting where the running CTAs currently are (g_knn2_front).
+// Where the time goes now (1.3M x 50, k = 15): 1000-1100 cycles per tile against the 512 of the tensor pipe.  The
+// examine phases cost each warp ~600 cycles per tile (~290 of them the ALU pipe's floor for the max trees: FMNMX3 issues
+// every 2 cycles per scheduler, FMNMX every cycle), and ~6 % of the chunk scans take the insertion path (~150 dependent
+// instructions for one lane); since the release of an accumulator buffer needs all 16 warps, whichever warp is inserting
+// gates the hand-off of nearly every tile.  Two decouplings were built, measured and dropped (git history):
+//   - scanners that push (row, id, score) into a shared-memory queue drained by inserter warps holding one list per row:
+//     exact, but the claim / release-acquire traffic cost more than it saved (1330 cycles per tile);
+//   - both chunks loaded before anything is examined and the sub-lists kept in shared memory (early release): the
+//     insertion walk over shared memory and the 96-register cap (18 warps) made each examine phase slower (1180-1240).
 #include <cuda_fp16.h>
 #include <float.h>
 
@@ -247,10 +258,13 @@ __device__ __forceinline__ void est_chunk(float (&est)[LEN], const uint32_t (&v)
 // NOSCAN (timing experiments only, SB2_KNN2_NOSCAN=1): the epilogue loads and releases but does not examine.
 // SB2_KNN2_STAMP=1: CTA 0, warp 2 records clock64 / globaltimer around its visit loop (cycles per visit and the SM clock
 // actually delivered under this kernel's load); read back by knn_tc2_sweep and printed to stderr
+// Sweep front: CTAs walk the candidate tiles cyclically, each starting where the CTAs already running currently are
+// (the order of the candidates is irrelevant to the result).  All resident CTAs then stream the same few tiles at the
+// same time and the candidate images (166 MB at 1.3M x 50, more than the L2) are read from HBM about once per wave of
+// CTAs instead of once per CTA.
+__device__ int32_t g_knn2_front;
 __device__ unsigned long long g_knn2_stamp[4];
 __device__ unsigned long long g_knn2_phase[2][8];
-__device__ long long g_knn2_tl[8][24];   // MODE 3: absolute clock64 of visits TL0..TL0+7: [visit][0 full ok,1 tempty ok,2 issued | 4+w: tfull seen by warp w (0..7 -> warps 0,1,2,3,12,13,14,15) | 12+w: released]
-constexpr int TL0 = 2000;   // MODE 2: cycles spent per phase by warps 2 and 5 of the middle CTA
 __device__ __forceinline__ unsigned long long gtimer_ns() {
   unsigned long long t;
   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
@@ -275,7 +289,8 @@ knn_sweep2_kernel(const __half* __restrict__ Aimg, const __half* __restrict__ Bi
   uint64_t* tfull = bars + 2 * MAXST + 1;    // [2] MMA (commit) -> epilogue
   uint64_t* tempty = bars + 2 * MAXST + 3;   // [2] epilogue (16 warps) -> MMA
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * MAXST + 5);
-  static_assert((2 * MAXST + 5) * 8 + 4 <= BAR_BYTES, "barrier block");
+  int32_t* start_tile = reinterpret_cast<int32_t*>(bars + 2 * MAXST + 6);
+  static_assert((2 * MAXST + 6) * 8 + 4 <= BAR_BYTES, "barrier block");
   float* est_x = reinterpret_cast<float*>(Bs0 + (size_t)nstage * part_b);  // [QM][NQUART][EST_R], present iff n_est > 0
 
   // warp index through a shuffle: tells the compiler it is warp-uniform, so each role's branch is a converged region
@@ -285,6 +300,8 @@ knn_sweep2_kernel(const __half* __restrict__ Aimg, const __half* __restrict__ Bi
     mbar_init(afull, 1);
     for (int b = 0; b < 2; ++b) { mbar_init(&tfull[b], 1); mbar_init(&tempty[b], NEPI); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    const int32_t f = *reinterpret_cast<volatile int32_t*>(&g_knn2_front);
+    *start_tile = (f >= 0 && (int64_t)f < n_btiles) ? f : 0;
   }
   if (warp == W_MMA) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u) : "memory");
@@ -305,8 +322,10 @@ knn_sweep2_kernel(const __half* __restrict__ Aimg, const __half* __restrict__ Bi
       int s = 0;
       uint32_t use_phase = 1;  // parity of the previous use of stage s (first lap: nothing to wait for)
       bool first_lap = true;
+      int64_t cs = *start_tile;   // cyclic walk of the sweep proper
       for (int64_t v = 0; v < n_est + n_btiles; ++v) {
-        const int64_t c = v < n_est ? v * est_stride : v - n_est;
+        int64_t c = v * est_stride;
+        if (v >= n_est) { c = cs; if (++cs == n_btiles) cs = 0; }
         for (int p = 0; p < nsplit; ++p) {
           if (!first_lap) mbar_wait(&empty[s], use_phase);
           mbar_expect_tx(&full[s], part_b);
@@ -341,10 +360,8 @@ knn_sweep2_kernel(const __half* __restrict__ Aimg, const __half* __restrict__ Bi
       for (int p = 0; p < nsplit; ++p) {
         mbar_wait(&full[s], ring_phase);
         SB2_MPH(0)
-        if (MODE == 3 && blockIdx.x == gridDim.x / 2 && lane == 0 && c >= TL0 && c < TL0 + 8) g_knn2_tl[c - TL0][0] = clock64();
         if (p == 0 && useb > 0) mbar_wait(&tempty[b], (uint32_t)((useb - 1) & 1));
         SB2_MPH(1)
-        if (MODE == 3 && blockIdx.x == gridDim.x / 2 && lane == 0 && c >= TL0 && c < TL0 + 8) g_knn2_tl[c - TL0][1] = clock64();
         tc_fence_after();
         const uint32_t tm = (uint32_t)(b * CN);  // the CTA owns all 512 TMEM columns: allocation starts at column 0
         uint32_t da = a_lo0 + (uint32_t)(p * nks) * KSTEP_A16;
@@ -361,7 +378,6 @@ knn_sweep2_kernel(const __half* __restrict__ Aimg, const __half* __restrict__ Bi
       }
       tc_commit_elect(&tfull[b]);     // accumulator buffer b complete
       SB2_MPH(2)
-      if (MODE == 3 && blockIdx.x == gridDim.x / 2 && lane == 0 && c >= TL0 && c < TL0 + 8) g_knn2_tl[c - TL0][2] = clock64();
     }
 #undef SB2_MPH
     if (PHASES_M && blockIdx.x == gridDim.x / 2 && lane == 0) {
@@ -399,7 +415,9 @@ knn_sweep2_kernel(const __half* __restrict__ Aimg, const __half* __restrict__ Bi
     uint32_t v[32];
     const uint32_t lane_base = tmem_base + ((uint32_t)(lgrp * 32) << 16) + (uint32_t)(cq * 64);
     const int n_visit = mma_visits, n_est_i = (int)n_est;
-    int32_t cbase = cq * 64;
+    int32_t ctile = *start_tile;                 // candidate tile of the current sweep visit (cyclic walk)
+    int32_t cbase = ctile * CN + cq * 64;
+    const int32_t n_bt = (int32_t)n_btiles;
     const bool stamp = blockIdx.x == gridDim.x / 2 && warp == 2 && lane == 0;
     unsigned long long st_c = 0, st_t = 0;
     if (stamp) { st_c = clock64(); st_t = gtimer_ns(); }
@@ -414,8 +432,6 @@ knn_sweep2_kernel(const __half* __restrict__ Aimg, const __half* __restrict__ Bi
       mbar_wait(&tfull[b], (uint32_t)((c >> 1) & 1));
       tc_fence_after();
       SB2_PH(0)
-      const bool tlw = MODE == 3 && blockIdx.x == gridDim.x / 2 && lane == 0 && (warp < 4 || warp >= 12) && c >= TL0 && c < TL0 + 8;
-      if (tlw) g_knn2_tl[c - TL0][4 + (warp < 4 ? warp : warp - 8)] = clock64();
       const uint32_t taddr = lane_base + (uint32_t)(b * CN);
       tmem_ld32_nowait(taddr, v);
       tmem_wait_ld();
@@ -453,10 +469,13 @@ knn_sweep2_kernel(const __half* __restrict__ Aimg, const __half* __restrict__ Bi
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty[b]);
       SB2_PH(4)
-      if (tlw) g_knn2_tl[c - TL0][12 + (warp < 4 ? warp : warp - 8)] = clock64();
       if (!NOSCAN) { if (estimating) est_chunk(L.ls, v); else scan_chunk(L, id, v, cbase + 32, n_points); }
       SB2_PH(5)
-      if (!estimating) cbase += CN;
+      if (!estimating) {
+        if ((c & 15) == 0 && warp == 0 && lane == 0) *reinterpret_cast<volatile int32_t*>(&g_knn2_front) = ctile;   // publish the front
+        cbase += CN;
+        if (++ctile == n_bt) { ctile = 0; cbase = cq * 64; }
+      }
     }
 #undef SB2_PH
     if (phw) {
@@ -558,9 +577,14 @@ int32_t knn_tc2_sweep(sb2_ctx* ctx, const KnnTc2Shape& sh, const __half* Aimg, i
   const int32_t np = (int32_t)n_points;
   const char* ns_env = getenv("SB2_KNN2_NOSCAN");   // timing experiments: 1 = epilogue loads but does not examine, 2 = per-phase cycle stamps
   const int mode = ns_env ? atoi(ns_env) : 0;
+  {
+    void* fp = nullptr;
+    SB2_CUDA(cudaGetSymbolAddress(&fp, g_knn2_front));
+    SB2_CUDA(cudaMemsetAsync(fp, 0, sizeof(int32_t), st));
+  }
   cudaError_t le;
 #define SB2_L2(NGV, MODEV) launch2<NGV, MODEV>(grid, sh, st, Aimg, Bimg, n_tiles, n_est, est_stride, a_tile0, n_query, np, cand_score, cand_idx)
-  if (list_m == 64) le = mode == 1 ? SB2_L2(2, 1) : (mode == 2 ? SB2_L2(2, 2) : (mode == 3 ? SB2_L2(2, 3) : SB2_L2(2, 0)));
+  if (list_m == 64) le = mode == 1 ? SB2_L2(2, 1) : (mode == 2 ? SB2_L2(2, 2) : SB2_L2(2, 0));
   else le = SB2_L2(4, 0);
 #undef SB2_L2
   SB2_CUDA(le);
@@ -579,18 +603,6 @@ int32_t knn_tc2_sweep(sb2_ctx* ctx, const KnnTc2Shape& sh, const __half* Aimg, i
         fprintf(stderr, "[knn2 phases] warp %d cycles/visit: wait tfull %.0f | ld0 %.0f | scan0 %.0f | ld1 %.0f | release %.0f | scan1 %.0f\n", w ? 5 : 2,
                 (double)p[w][0] / h[2], (double)p[w][1] / h[2], (double)p[w][2] / h[2], (double)p[w][3] / h[2], (double)p[w][4] / h[2], (double)p[w][5] / h[2]);
       ;
-    }
-    if (mode == 3 && h[2] > (unsigned long long)(TL0 + 8)) {
-      long long tl[8][24];
-      SB2_CUDA(cudaMemcpyFromSymbol(tl, g_knn2_tl, sizeof(tl)));
-      const long long t0 = tl[0][1];
-      for (int v = 0; v < 8; ++v) {
-        fprintf(stderr, "[knn2 timeline] visit %d: issuer full_ok %6lld tempty_ok %6lld issued %6lld | tfull seen", TL0 + v, tl[v][0] - t0, tl[v][1] - t0, tl[v][2] - t0);
-        for (int w = 0; w < 8; ++w) fprintf(stderr, " %6lld", tl[v][4 + w] - t0);
-        fprintf(stderr, " | released");
-        for (int w = 0; w < 8; ++w) fprintf(stderr, " %6lld", tl[v][12 + w] - t0);
-        fprintf(stderr, "\n");
-      }
     }
     if (mode == 2 && h[2] > 0) {
       unsigned long long p[2][8];

@@ -19,4 +19,4 @@ def run(tag, reps=3, **env):
     sm = subprocess.run(["nvidia-smi", "--query-gpu=clocks.sm,power.draw", "--format=csv,noheader"], capture_output=True, text=True).stdout.strip()
     print(tag, {k: info[k] for k in ("pass1_ms", "pass1_issued_flops", "n_resweep")}, "issued TF/s", info["pass1_issued_flops"] / info["pass1_ms"] / 1e9, "| after:", sm, flush=True)
     for k in env: os.environ.pop(k)
-run("v2 timeline", reps=1, SB2_KNN2_NOSCAN="3")
+run("v2 phases", reps=1, SB2_KNN2_NOSCAN="2")
