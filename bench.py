@@ -25,7 +25,7 @@ from pathlib import Path
 
 # the numpy / scipy wheels bundle an OpenBLAS built for at most 64 threads: on a box with more cores it warns and can
 # crash in large GEMMs ("Bad memory unallocation") unless its pool is capped BEFORE the library loads
-os.environ.setdefault("OPENBLAS_NUM_THREADS", str(min(64, os.cpu_count() or 1)))
+os.environ.setdefault("OPENBLAS_NUM_THREADS", str(min(32, os.cpu_count() or 1)))
 
 import numpy as np
 
@@ -47,6 +47,9 @@ def parse_args():
     p.add_argument("--n-pcs", type=int, default=50)
     p.add_argument("--k", type=int, default=15)
     p.add_argument("--no-cpu-baseline", action="store_true")
+    p.add_argument("--cpu-sample", action="store_true", help="(internal) print one cpu_reference_sample dict as JSON and exit")
+    p.add_argument("--sample-rows", type=int, default=100_000)
+    p.add_argument("--knn-queries", type=int, default=8192)
     p.add_argument("--no-e2e", action="store_true")
     p.add_argument("--no-parity", action="store_true", help="skip the host-side fp64 parity checks after the timed region")
     return p.parse_args()
@@ -66,15 +69,15 @@ def workload_config(a, n_gpus):
 def _all_cores():
     """BLAS / OpenMP threads = every core of the box, whatever the launcher exported (torch.distributed.run forces
     OMP_NUM_THREADS=1 into its workers, which would otherwise cut the CPU arm to a single thread)."""
-    n = os.cpu_count() or 1
-    os.environ["OMP_NUM_THREADS"] = str(min(n, 64))
+    n = int(os.environ.get("SB2_CPU_THREADS", min(os.cpu_count() or 1, 32)))
+    os.environ["OMP_NUM_THREADS"] = str(n)
     try:
         from threadpoolctl import threadpool_limits
 
-        # sklearn's brute-force kNN runs one BLAS call per OpenMP thread: the bundled OpenBLAS builds (64 / 128 buffer
-        # regions) abort when more threads than that call into them at once
-        threadpool_limits(limits=min(n, 64), user_api="openmp")
-        threadpool_limits(limits=min(n, 64), user_api="blas")
+        # sklearn's brute-force kNN runs one BLAS call per OpenMP thread: the bundled OpenBLAS builds abort when too many
+        # threads call into them at once, so OpenMP gets n threads and every caller a single BLAS thread
+        threadpool_limits(limits=n, user_api="openmp")
+        threadpool_limits(limits=1, user_api="blas")
     except Exception:
         pass
     try:
@@ -83,7 +86,7 @@ def _all_cores():
         torch.set_num_threads(n)
     except Exception:
         pass
-    return min(n, 64)
+    return n
 
 
 def note(msg: str) -> None:
@@ -133,13 +136,44 @@ def cpu_reference_sample(a, sample_rows: int = 100_000, knn_queries: int = 8192)
                 stage_seconds_extrapolated=est)
 
 
+def cpu_reference_subprocess(a, sample_rows: int | None = None, knn_queries: int | None = None):
+    """cpu_reference_sample in a FRESH interpreter: thread-pool sizes are fixed by the environment before numpy / scipy /
+    sklearn / torch load their BLAS and OpenMP runtimes (inside this process torch has already loaded its own, and the
+    launcher may have exported OMP_NUM_THREADS=1), and a crash of a CPU library cannot take the bench line with it."""
+    cmd = [sys.executable, str(ROOT / "bench.py"), "--cpu-sample", "--n-cells", str(a.n_cells), "--n-genes", str(a.n_genes),
+           "--n-pcs", str(a.n_pcs), "--k", str(a.k)]
+    if sample_rows:
+        cmd += ["--sample-rows", str(sample_rows)]
+    if knn_queries:
+        cmd += ["--knn-queries", str(knn_queries)]
+    err = ""
+    # sklearn's brute-force kNN calls BLAS from every OpenMP thread; the OpenBLAS builds bundled with numpy / scipy abort
+    # ("too many memory regions") beyond a few dozen concurrent callers, so: OpenMP threads = min(cores, 32), one BLAS
+    # thread per caller - and fewer if even that fails on this host
+    for omp in (32, 16, 8):
+        omp = min(omp, os.cpu_count() or 1)
+        env = dict(os.environ, OMP_NUM_THREADS=str(omp), OPENBLAS_NUM_THREADS="1", MKL_NUM_THREADS="1",
+                   CUDA_VISIBLE_DEVICES=os.environ.get("CUDA_VISIBLE_DEVICES", ""), SB2_CPU_THREADS=str(omp))
+        for k in ("RANK", "WORLD_SIZE", "LOCAL_RANK", "MASTER_ADDR", "MASTER_PORT", "TORCHELASTIC_RUN_ID"):
+            env.pop(k, None)
+        r = subprocess.run(cmd, capture_output=True, text=True, env=env, timeout=900)
+        for line in reversed(r.stdout.strip().splitlines()):
+            if line.startswith("{"):
+                return json.loads(line)
+        err = f"rc {r.returncode}: {r.stderr.strip()[-200:]}"
+    return dict(value=None, unit=UNIT, kind="port", error=f"cpu sample failed ({err})")
+
+
 def run_reference(a, rank, world):
     if rank != 0:
         return
     t0 = time.perf_counter()
     for _ in range(max(a.warmup, 0)):
-        cpu_reference_sample(a, sample_rows=8000, knn_queries=256)  # warm caches / thread pools cheaply
-    vals = [cpu_reference_sample(a) for _ in range(max(a.steps, 1))]
+        cpu_reference_subprocess(a, sample_rows=8000, knn_queries=256)  # warm the page cache cheaply
+    vals = [v for v in (cpu_reference_subprocess(a) for _ in range(max(a.steps, 1))) if v.get("value")]
+    if not vals:
+        emit(json.dumps(dict(impl="reference", unavailable="the CPU sample failed on this host")))
+        return
     order = sorted(vals, key=lambda r: r["value"])
     med = order[len(order) // 2]
     v = float(med["value"])
@@ -385,7 +419,7 @@ def run_b200(a, rank, world, local_rank):
         line["stages"]["parity"] = parity_checks(a, out, x_local if world == 1 else None, labels_local, (r0, r1))
     if world == 1 and not a.no_cpu_baseline:
         note("cpu baseline sample")
-        line["cpu_baseline"] = cpu_reference_sample(a)
+        line["cpu_baseline"] = cpu_reference_subprocess(a)
     emit(json.dumps(line))
 
 
@@ -406,6 +440,9 @@ def main():
     rank = int(os.environ.get("RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))
     local_rank = int(os.environ.get("LOCAL_RANK", 0))
+    if a.cpu_sample:
+        emit(json.dumps(cpu_reference_sample(a, sample_rows=a.sample_rows, knn_queries=a.knn_queries)))
+        return
     if a.impl == "reference":
         os.environ["OMP_NUM_THREADS"] = str(min(64, os.cpu_count() or 1))   # before sklearn / torch load their OpenMP runtimes
         os.environ.pop("MKL_NUM_THREADS", None)

@@ -106,8 +106,8 @@ decide_kernel(Level L, const int32_t* __restrict__ wl, int32_t w_begin, int32_t 
   if (!REFINE) {
     if (noskip == 0) {
       // the vertices are dealt into 2^cshift pseudo-random classes (re-dealt every 2^cshift sweeps); a sweep lets ONE class
-      // decide, so a vertex always sees the moves of the other classes: 2 classes on big levels (throughput), 8 on small
-      // ones (closer to the sequential algorithm's one-vertex-at-a-time semantics, where sweeps cost microseconds)
+      // decide, so a vertex always sees the moves of the other classes: 2 classes normally, 8 for small input graphs
+      // (closer to the sequential algorithm's one-vertex-at-a-time semantics, where sweeps cost microseconds)
       const uint32_t cls = (mix32((uint32_t)v * 0x9E3779B9U + seed * 0x85EBCA6BU + (uint32_t)(sweep >> cshift)) + (uint32_t)sweep) & ((1u << cshift) - 1u);
       if (cls) { if (lane == 0) target[oi] = -2; return; }
     }
@@ -224,11 +224,11 @@ __global__ void compact_flags_kernel(int32_t n, const int32_t* __restrict__ flag
 
 __global__ void lm_apply_kernel(Level L, const int32_t* __restrict__ wl, int32_t n_wl, int32_t* __restrict__ comm,
                                 const int32_t* __restrict__ target, u64* __restrict__ K, int32_t* __restrict__ csize,
-                                int32_t* __restrict__ in_next, u64* __restrict__ counters, uint32_t salt) {
+                                int32_t* __restrict__ in_next, u64* __restrict__ counters, uint32_t salt, int independent) {
   // counters[0]: accepted moves of this sweep.  in_next[u] = 1 marks the next sweep's active vertices (those skipped by
   // this half-sweep, those deferred + the neighbours of every moved vertex); the list itself is built by a prefix sum
   // over the flags, so it is sorted by vertex id - identical on every rank and from run to run.
-  // Independent-set rule: of two ADJACENT vertices that both decided to move, only the one with the higher (salted
+  // Independent-set rule (small input graphs only, `independent`): of two ADJACENT vertices that both decided to move, only the one with the higher (salted
   // hash) priority moves in this sweep; the other stays active and decides again against the new state.  A move's gain
   // was computed from its neighbours' communities - which therefore did not change under it - so simultaneous moves can
   // no longer undo each other (the classic failure of synchronous Louvain / Leiden sweeps).
@@ -240,7 +240,7 @@ __global__ void lm_apply_kernel(Level L, const int32_t* __restrict__ wl, int32_t
   if (t < 0) return;
   const int64_t e0 = L.indptr[v], e1 = L.indptr[v + 1];
   const uint32_t pv = mix32((uint32_t)v * 0x9E3779B9U + salt);
-  for (int64_t e = e0; e < e1; ++e) {
+  for (int64_t e = e0; independent && e < e1; ++e) {
     const int32_t u = L.indices[e];
     if (u == v || target[u] < 0) continue;
     const uint32_t pu = mix32((uint32_t)u * 0x9E3779B9U + salt);
@@ -452,6 +452,8 @@ struct Work {
   int64_t moves_total;
   int last_sweeps;
   bool first_pass;
+  bool careful;     // small INPUT graphs (n0 < CAREFUL_N): 8 vertex classes per round of sweeps + independent-set rule - closer
+                    // to the sequential algorithm, at a cost in sweeps that only a graph this small can afford
   bool exact;       // SB2_LEIDEN_EXACT=1: no first-pass / refinement cut-offs (every phase runs to its fixed point)
 };
 
@@ -470,7 +472,7 @@ template <bool REFINE>
 int32_t decide(Work& w, const Level& L, const int32_t* wl, int32_t n_wl, const int32_t* comm, const int32_t* ref, const int64_t* K,
                const int32_t* csize, int sweep, int noskip) {
   sb2_ctx* ctx = w.ctx;
-  const int cshift = L.n <= 32768 ? 3 : (L.n <= 262144 ? 2 : 1);   // classes per round of sweeps (decide_kernel)
+  const int cshift = w.careful ? 3 : 1;   // 2^cshift vertex classes per round of sweeps (decide_kernel)
   const int P = ctx->nccl_comm ? ctx->n_ranks : 1;
   if (P == 1 || n_wl < SHARD_MIN) {
     decide_kernel<REFINE><<<gridw(n_wl), 256, 0, w.st>>>(L, wl, 0, n_wl, comm, ref, K, csize, w.gamma, w.total, w.seed, sweep, noskip,
@@ -527,7 +529,7 @@ int32_t local_move(Work& w, const Level& L, int32_t* comm, int64_t* moves_out) {
     SB2_CUDA(cudaMemsetAsync(w.counter, 0, 2 * sizeof(u64), w.st));
     SB2_TRY(decide<false>(w, L, w.wl[cur], n_wl, comm, nullptr, (const int64_t*)w.K, w.csize, sweep, noskip));
     lm_apply_kernel<<<gridt(n_wl), 256, 0, w.st>>>(L, w.wl[cur], n_wl, comm, w.target, w.K, w.csize, w.in_next, w.counter,
-                                                   w.seed * 0x85EBCA6BU + (uint32_t)sweep);
+                                                   w.seed * 0x85EBCA6BU + (uint32_t)sweep, w.careful ? 1 : 0);
     SB2_LAUNCH_CHECK(ctx);
     reset_targets_kernel<<<gridt(n_wl), 256, 0, w.st>>>(w.wl[cur], n_wl, w.target);
     SB2_LAUNCH_CHECK(ctx);
@@ -751,6 +753,7 @@ static int32_t leiden_core(sb2_ctx* ctx, int64_t n, const int64_t* d_indptr, con
   w.ctx = ctx; w.st = st; w.n0 = n0; w.gamma = resolution; w.total = total;
   w.seed = (uint32_t)(seed ^ (seed >> 32));
   { const char* ex = getenv("SB2_LEIDEN_EXACT"); w.exact = ex && atoi(ex) > 0; }
+  w.careful = n0 < 65536;
   SB2_TRY(scr.alloc(&w.K, (size_t)n0));
   SB2_TRY(scr.alloc(&w.csize, (size_t)n0));
   SB2_TRY(scr.alloc(&w.hkeys, (size_t)std::max<int64_t>(nnz0, 1)));
