@@ -324,6 +324,111 @@ __global__ void col_absmax_kernel(const double* __restrict__ U, int g, int l, do
 }
 
 // ---------------------------------------------------------------------------------------------
+// Rayleigh-Ritz eigenproblem on the device: S (m x m, m = block width <= 64, symmetrised on load) -> eigenvalues in
+// descending order and the matching eigenvectors (columns of W).  One CTA, two-sided Jacobi with the round-robin
+// ("tournament") ordering: every step rotates m/2 disjoint index pairs at once - rotation angles, column update of A and
+// V, row update of A - so a sweep is m-1 steps of three barriers instead of m(m-1)/2 sequential rotations.  Replaces the
+// host-side cyclic Jacobi (a few milliseconds of single-threaded CPU work and a device round trip per Rayleigh-Ritz step,
+// replicated on every rank).
+__global__ void __launch_bounds__(256)
+rr_jacobi_kernel(const double* __restrict__ S, int m, double* __restrict__ W, double* __restrict__ theta) {
+  extern __shared__ double sm[];
+  const int ld = m + 1;
+  double* A = sm;                 // [m][ld]
+  double* V = A + (size_t)m * ld;  // [m][ld]
+  double* cs = V + (size_t)m * ld;  // [m/2]
+  double* sn = cs + m / 2;         // [m/2]
+  double* red = sn + m / 2;        // [256] reduction scratch, then eigenvalues
+  int* top = reinterpret_cast<int*>(red + 256);  // [m/2]
+  int* bot = top + m / 2;                        // [m/2]
+  __shared__ int done;
+  const int tid = threadIdx.x, nt = blockDim.x, half = m / 2;
+  for (int i = tid; i < m * m; i += nt) {
+    const int r = i / m, c = i % m;
+    A[r * ld + c] = 0.5 * (S[r * m + c] + S[c * m + r]);
+    V[r * ld + c] = r == c ? 1.0 : 0.0;
+  }
+  for (int p = tid; p < half; p += nt) { top[p] = 2 * p; bot[p] = 2 * p + 1; }
+  __syncthreads();
+  for (int sweep = 0; sweep < 40; ++sweep) {
+    double off = 0.0, dg = 0.0;
+    for (int i = tid; i < m * m; i += nt) {
+      const int r = i / m, c = i % m;
+      const double a = A[r * ld + c];
+      if (r == c) dg += a * a; else if (c > r) off += a * a;
+    }
+    red[tid] = off;
+    __syncthreads();
+    for (int k = nt / 2; k > 0; k >>= 1) { if (tid < k) red[tid] += red[tid + k]; __syncthreads(); }
+    const double offs = red[0];
+    __syncthreads();
+    red[tid] = dg;
+    __syncthreads();
+    for (int k = nt / 2; k > 0; k >>= 1) { if (tid < k) red[tid] += red[tid + k]; __syncthreads(); }
+    if (tid == 0) done = (offs <= 1e-30 * (red[0] + offs) || offs == 0.0) ? 1 : 0;
+    __syncthreads();
+    if (done) break;
+    for (int step = 0; step < m - 1; ++step) {
+      if (tid < half) {
+        const int a = top[tid], b = bot[tid];
+        const int i = min(a, b), j = max(a, b);
+        const double apq = A[i * ld + j];
+        double c = 1.0, sv = 0.0;
+        if (fabs(apq) >= 1e-300) {
+          const double tau = (A[j * ld + j] - A[i * ld + i]) / (2.0 * apq);
+          const double t = (tau >= 0.0 ? 1.0 : -1.0) / (fabs(tau) + sqrt(1.0 + tau * tau));
+          c = 1.0 / sqrt(1.0 + t * t);
+          sv = t * c;
+        }
+        cs[tid] = c; sn[tid] = sv;
+      }
+      __syncthreads();
+      for (int it = tid; it < half * m; it += nt) {   // columns i, j of A and V
+        const int p = it / m, k = it % m;
+        const int a = top[p], b = bot[p];
+        const int i = min(a, b), j = max(a, b);
+        const double c = cs[p], sv = sn[p];
+        const double aki = A[k * ld + i], akj = A[k * ld + j];
+        A[k * ld + i] = c * aki - sv * akj;
+        A[k * ld + j] = sv * aki + c * akj;
+        const double vki = V[k * ld + i], vkj = V[k * ld + j];
+        V[k * ld + i] = c * vki - sv * vkj;
+        V[k * ld + j] = sv * vki + c * vkj;
+      }
+      __syncthreads();
+      for (int it = tid; it < half * m; it += nt) {   // rows i, j of A
+        const int p = it / m, k = it % m;
+        const int a = top[p], b = bot[p];
+        const int i = min(a, b), j = max(a, b);
+        const double c = cs[p], sv = sn[p];
+        const double aik = A[i * ld + k], ajk = A[j * ld + k];
+        A[i * ld + k] = c * aik - sv * ajk;
+        A[j * ld + k] = sv * aik + c * ajk;
+      }
+      __syncthreads();
+      if (tid == 0) {   // rotate the tournament: top[0] stays, everybody else moves one seat
+        const int last_top = top[half - 1], first_bot = bot[0];
+        for (int p = half - 1; p > 1; --p) top[p] = top[p - 1];
+        if (half > 1) top[1] = first_bot;
+        for (int p = 0; p < half - 1; ++p) bot[p] = bot[p + 1];
+        bot[half - 1] = half > 1 ? last_top : first_bot;
+      }
+      __syncthreads();
+    }
+  }
+  // eigenvalues, sorted descending (ties: smaller index first), eigenvectors permuted accordingly
+  for (int i = tid; i < m; i += nt) red[i] = A[i * ld + i];
+  __syncthreads();
+  for (int i = tid; i < m; i += nt) {
+    const double wi = red[i];
+    int rank = 0;
+    for (int j = 0; j < m; ++j) rank += (red[j] > wi || (red[j] == wi && j < i)) ? 1 : 0;
+    theta[rank] = wi;
+    for (int k = 0; k < m; ++k) W[(size_t)k * m + rank] = V[k * ld + i];
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 // host fp64 small dense algebra
 // cyclic Jacobi: A (m x m symmetric, row-major, destroyed) -> eigenvalues w, eigenvectors V (columns)
 void jacobi_eigh(std::vector<double>& A, int m, std::vector<double>& w, std::vector<double>& V) {
@@ -497,6 +602,28 @@ int32_t right_mult_inplace(PcaWork& w, double* A, const std::vector<double>& hM)
                                                                                                   w.d_tmp);
   SB2_LAUNCH_CHECK(w.ctx);
   SB2_CUDA(cudaMemcpyAsync(A, w.d_tmp, sizeof(double) * (size_t)w.g * l, cudaMemcpyDeviceToDevice, w.st));
+  return SB2_OK;
+}
+// A <- A * M with M already on the device (l x l)
+int32_t right_mult_device(PcaWork& w, double* A, const double* dM) {
+  const int l = w.l;
+  right_mult_kernel<<<(unsigned)ceil_div64((int64_t)w.g * l, 256), 256, sizeof(double) * l * l, w.st>>>(A, dM, w.g, l, l, w.d_tmp);
+  SB2_LAUNCH_CHECK(w.ctx);
+  SB2_CUDA(cudaMemcpyAsync(A, w.d_tmp, sizeof(double) * (size_t)w.g * l, cudaMemcpyDeviceToDevice, w.st));
+  return SB2_OK;
+}
+size_t rr_jacobi_smem(int l) { return sizeof(double) * (2 * (size_t)l * (l + 1) + l + 256) + sizeof(int) * l; }
+// Rayleigh-Ritz on the device: S = V^T Z, eigen-decomposition (rr_jacobi_kernel), V <- V W, Z <- Z W; d_theta receives the
+// Ritz values (descending).  Nothing travels to the host.
+int32_t rayleigh_ritz_device(PcaWork& w, double* V, double* Z, double* d_theta) {
+  const int l = w.l;
+  SB2_CUDA(cudaMemsetAsync(w.d_S, 0, sizeof(double) * l * l, w.st));
+  tsmm_tn_kernel<<<(unsigned)ceil_div64(w.g, 32), 256, sizeof(double) * 2 * 32 * l, w.st>>>(V, Z, w.g, l, w.d_S);
+  SB2_LAUNCH_CHECK(w.ctx);
+  rr_jacobi_kernel<<<1, 256, rr_jacobi_smem(l), w.st>>>(w.d_S, l, w.d_M, d_theta);
+  SB2_LAUNCH_CHECK(w.ctx);
+  SB2_TRY(right_mult_device(w, V, w.d_M));
+  SB2_TRY(right_mult_device(w, Z, w.d_M));
   return SB2_OK;
 }
 // orthonormalise the columns of A (g x l): CholeskyQR, twice; eigen-based fallback if rank deficient
@@ -746,6 +873,7 @@ int32_t sb2_pca_csr_f32(sb2_ctx* ctx, int64_t n, int64_t n_total, int32_t g, con
   }
   SB2_CUDA(cudaFuncSetAttribute(tsmm_tn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(double) * 2 * 32 * l)));
   SB2_CUDA(cudaFuncSetAttribute(right_mult_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(double) * l * l)));
+  if (l <= 64) SB2_CUDA(cudaFuncSetAttribute(rr_jacobi_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rr_jacobi_smem(l)));
 
   // ---- start block (identical on every rank: same seed) ----
   Rng rng(seed);
@@ -779,17 +907,22 @@ int32_t sb2_pca_csr_f32(sb2_ctx* ctx, int64_t n, int64_t n_total, int32_t g, con
     SB2_TRY(apply_operator(w, d_V, d_Z));
     ++it;
     {
-      SB2_TRY(tsmm_host(w, d_V, d_Z, T));
-      for (int i = 0; i < l; ++i)  // symmetrise
-        for (int j = i + 1; j < l; ++j) {
-          const double a = 0.5 * (T[(size_t)i * l + j] + T[(size_t)j * l + i]);
-          T[(size_t)i * l + j] = T[(size_t)j * l + i] = a;
-        }
-      jacobi_eigh(T, l, theta, W);
-      sort_desc(theta, W, l);
-      SB2_TRY(right_mult_inplace(w, d_V, W));  // V <- Ritz vectors
-      SB2_TRY(right_mult_inplace(w, d_Z, W));  // Z <- A * Ritz vectors
-      SB2_CUDA(cudaMemcpyAsync(d_theta, theta.data(), sizeof(double) * l, cudaMemcpyHostToDevice, st));
+      if (l <= 64) {
+        // Rayleigh-Ritz entirely on the device; the Ritz values come back together with the residual norms (one sync)
+        SB2_TRY(rayleigh_ritz_device(w, d_V, d_Z, d_theta));
+      } else {
+        SB2_TRY(tsmm_host(w, d_V, d_Z, T));
+        for (int i = 0; i < l; ++i)  // symmetrise
+          for (int j = i + 1; j < l; ++j) {
+            const double a = 0.5 * (T[(size_t)i * l + j] + T[(size_t)j * l + i]);
+            T[(size_t)i * l + j] = T[(size_t)j * l + i] = a;
+          }
+        jacobi_eigh(T, l, theta, W);
+        sort_desc(theta, W, l);
+        SB2_TRY(right_mult_inplace(w, d_V, W));  // V <- Ritz vectors
+        SB2_TRY(right_mult_inplace(w, d_Z, W));  // Z <- A * Ritz vectors
+        SB2_CUDA(cudaMemcpyAsync(d_theta, theta.data(), sizeof(double) * l, cudaMemcpyHostToDevice, st));
+      }
       SB2_CUDA(cudaMemsetAsync(d_res, 0, sizeof(double) * l, st));
       {
         const int threads = (1024 / l) * l;
@@ -797,6 +930,10 @@ int32_t sb2_pca_csr_f32(sb2_ctx* ctx, int64_t n, int64_t n_total, int32_t g, con
         SB2_LAUNCH_CHECK(ctx);
       }
       SB2_CUDA(cudaMemcpyAsync(hres.data(), d_res, sizeof(double) * l, cudaMemcpyDeviceToHost, st));
+      if (l <= 64) {
+        theta.resize(l);
+        SB2_CUDA(cudaMemcpyAsync(theta.data(), d_theta, sizeof(double) * l, cudaMemcpyDeviceToHost, st));
+      }
       SB2_CUDA(cudaStreamSynchronize(st));
       max_rel = 0.0;
       const double th1 = std::max(theta[0], 1e-300);
