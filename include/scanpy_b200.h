@@ -172,6 +172,12 @@ int32_t sb2_leiden_csr_f32(sb2_ctx* ctx, int64_t n, const int64_t* d_indptr, con
 int32_t sb2_modularity_csr_f32(sb2_ctx* ctx, int64_t n, const int64_t* d_indptr, const int32_t* d_indices,
                                const float* d_weights, double resolution, const int32_t* d_membership,
                                double* h_modularity);
+/* Louvain: local moving + aggregation, no refinement, one pass to its fixed point - replaces
+ * `louvain.find_partition(g, RBConfigurationVertexPartition, ...)` / `g.community_multilevel(weights)` at
+ * src/scanpy/tools/_louvain.py:150-176.  Outputs as sb2_leiden_csr_f32. */
+int32_t sb2_louvain_csr_f32(sb2_ctx* ctx, int64_t n, const int64_t* d_indptr, const int32_t* d_indices,
+                            const float* d_weights, double resolution, uint64_t seed, int32_t* d_membership,
+                            double* h_modularity, int32_t* h_n_comms, sb2_leiden_info* info);
 
 /* ---- preprocessing passes in front of the path: normalize_total, log1p, HVG statistics ----
  * sb2_csr_row_sums_f32      <- numba `_normalize_csr` (src/scanpy/preprocessing/_normalization.py:29-66): per-cell
@@ -193,6 +199,28 @@ int32_t sb2_csr_scale_rows_f32(sb2_ctx* ctx, int64_t n, const int64_t* d_indptr,
 int32_t sb2_log1p_f32(sb2_ctx* ctx, int64_t nnz, float* d_data, double base);
 int32_t sb2_csr_col_sums_f32(sb2_ctx* ctx, int64_t nnz, int32_t g, const int32_t* d_indices, const float* d_data,
                              int32_t apply_expm1, double log_scale, double* d_sum, double* d_sumsq);
+
+
+/* ---- sc.pp.scale (SURVEY.md 8f row f2 tail; src/scanpy/preprocessing/_scale.py:150-296) ----
+ * sb2_csr_col_stats_rows_f32 <- mean_var(x[mask_obs, :], axis=0, correction=1): per-gene sum / sum of squares (fp64) over
+ *                               the rows with d_mask[row] != 0 (d_mask == NULL: every row)
+ * sb2_csr_scale_cols_f32     <- numba `scale_and_clip_csr` (:267-283): data[j] = min(max_value, data[j] / std[col]) on the
+ *                               masked rows, in place (zero_center=False keeps the matrix sparse)
+ * sb2_csr_scale_dense_f64    <- `x -= mean; x /= std; clip` on a CSR (:203-222): the dense float64 [n x g] result; rows
+ *                               outside d_mask keep their values
+ * sb2_dense_col_stats / sb2_dense_scale <- the same two steps for a dense float32 (is_f64 = 0) / float64 [n x g] input,
+ *                               in place; d_mean == NULL means zero_center=False (then only the upper clip applies) */
+int32_t sb2_csr_col_stats_rows_f32(sb2_ctx* ctx, int64_t n, int32_t g, const int64_t* d_indptr, const int32_t* d_indices,
+                                   const float* d_data, const uint8_t* d_mask, double* d_sum, double* d_sumsq);
+int32_t sb2_csr_scale_cols_f32(sb2_ctx* ctx, int64_t n, const int64_t* d_indptr, const int32_t* d_indices, float* d_data,
+                               const double* d_std, const uint8_t* d_mask, int32_t has_max, double max_value);
+int32_t sb2_csr_scale_dense_f64(sb2_ctx* ctx, int64_t n, int32_t g, const int64_t* d_indptr, const int32_t* d_indices,
+                                const float* d_data, const double* d_mean, const double* d_std, const uint8_t* d_mask,
+                                int32_t has_max, double max_value, double* d_out);
+int32_t sb2_dense_col_stats(sb2_ctx* ctx, int64_t n, int32_t g, const void* d_x, int32_t is_f64, const uint8_t* d_mask,
+                            double* d_sum, double* d_sumsq);
+int32_t sb2_dense_scale(sb2_ctx* ctx, int64_t n, int32_t g, void* d_x, int32_t is_f64, const double* d_mean,
+                        const double* d_std, const uint8_t* d_mask, int32_t has_max, double max_value);
 
 #ifdef __cplusplus
 }

@@ -101,3 +101,56 @@ def hvg_seurat_from_stats(mean, var, *, n_top_genes=None, min_disp=0.5, max_disp
         hv = np.nan_to_num(dn, nan=-np.inf) >= v[n - 1]
     df["highly_variable"] = hv
     return df.drop(columns=["mean_bin"])
+
+
+def scale(x, *, zero_center=True, max_value=None, mask_obs=None):
+    """`scale_array` / `scale_array_masked` / `clip_array` / `scale_and_clip_csr`
+    (src/scanpy/preprocessing/_scale.py:52-69,150-283) restated in numpy -> (x_scaled, mean, std).
+    Pinned by the reference's goldens in tests/test_scaling.py:15-53 (X_original / X_scaled_original /
+    X_centered_original and their clipped / masked variants, reproduced in tests/golden/)."""
+    sp = sparse.issparse(x)
+    if sp:
+        x = sparse.csr_matrix(x).copy()
+    else:
+        x = np.array(x, copy=True)
+    if np.issubdtype(x.dtype, np.integer):
+        x = x.astype(np.float64)
+    sel = slice(None) if mask_obs is None else np.asarray(mask_obs, bool)
+    sub = x[sel, :]
+    n = sub.shape[0]
+    if sp:
+        d64 = sub.astype(np.float64)
+        mean = np.asarray(d64.mean(axis=0)).ravel()
+        mean_sq = np.asarray(d64.multiply(d64).mean(axis=0)).ravel()
+    else:
+        mean = sub.mean(axis=0, dtype=np.float64)
+        mean_sq = np.multiply(sub, sub, dtype=np.float64).mean(axis=0, dtype=np.float64)
+    var = (mean_sq - mean**2) * (n / (n - 1))
+    std = np.sqrt(var)
+    std[std == 0] = 1
+    if sp and not zero_center:
+        rows = np.repeat(np.arange(x.shape[0]), np.diff(x.indptr))
+        on = np.ones(x.nnz, bool) if mask_obs is None else np.asarray(mask_obs, bool)[rows]
+        v = x.data.astype(np.float64) / std[x.indices]
+        if max_value is not None:
+            v = np.minimum(max_value, v)
+        x.data[on] = v[on].astype(x.dtype)
+        return x, mean, std
+    if sp:
+        assert mask_obs is None
+        out = np.asarray(x.astype(np.float64).todense()) - mean  # `x -= mean` on a sparse matrix -> float64 dense
+        out = out / std
+    else:
+        out = sub.copy()
+        if zero_center:
+            out -= mean  # in place: rounded to x.dtype
+        out /= std
+    if max_value is not None:
+        out[out > max_value] = max_value
+        if zero_center:
+            out[out < -max_value] = -max_value
+    if not sp and mask_obs is not None:
+        full = x.copy()
+        full[sel, :] = out
+        out = full
+    return out, mean, std

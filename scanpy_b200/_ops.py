@@ -273,6 +273,22 @@ def leiden(adj, *, resolution: float = 1.0, n_iterations: int = -1, seed: int = 
     return _to_host(member), q, info
 
 
+def louvain(adj, *, resolution: float = 1.0, seed: int = 0, ctx=None):
+    """Louvain on a symmetric scipy CSR adjacency -> (membership int32 [n], modularity, info)."""
+    ctx = ctx or _abi.default_context()
+    torch = _torch()
+    adj = adj.tocsr()
+    n = adj.shape[0]
+    d_indptr, d_indices, d_w = csr_to_device(adj)
+    member = torch.empty(n, dtype=torch.int32, device="cuda")
+    q = c_double()
+    nc = c_int32()
+    info = LeidenInfo()
+    check(ctx.lib.sb2_louvain_csr_f32(ctx.handle, n, ptr(d_indptr), ptr(d_indices), ptr(d_w), float(resolution), int(seed),
+                                      ptr(member), byref(q), byref(nc), byref(info)))
+    return _to_host(member), q.value, dict(levels=info.levels, moves=int(info.moves), n_communities=nc.value)
+
+
 def modularity(adj, membership, *, resolution: float = 1.0, ctx=None) -> float:
     ctx = ctx or _abi.default_context()
     adj = adj.tocsr()

@@ -181,3 +181,94 @@ def highly_variable_genes(adata, *, layer=None, n_top_genes: int | None = None, 
     if subset:
         df = df.iloc[df["highly_variable"].to_numpy(), :]
     return df
+
+
+def _scale_array(x, *, zero_center: bool, max_value, mask_obs):
+    """`scale_array` / `scale_array_masked` (src/scanpy/preprocessing/_scale.py:150-264) on the device.
+    -> (scaled x, mean float64[g], std float64[g])."""
+    import torch
+
+    ctx = _abi.default_context()
+    n, g = x.shape
+    has_max = 0 if max_value is None else 1
+    mx = 0.0 if max_value is None else float(max_value)
+    d_mask = None if mask_obs is None else _ops._to_device(np.ascontiguousarray(mask_obs, dtype=np.uint8))
+    n_sel = n if mask_obs is None else int(np.count_nonzero(mask_obs))
+    s1 = torch.empty(g, dtype=torch.float64, device="cuda")
+    s2 = torch.empty(g, dtype=torch.float64, device="cuda")
+    is_sparse = sparse.issparse(x)
+    if is_sparse:
+        xs = _as_csr32(x)
+        d_indptr, d_indices, d_data = _ops.csr_to_device(xs)
+        check(ctx.lib.sb2_csr_col_stats_rows_f32(ctx.handle, n, g, ptr(d_indptr), ptr(d_indices), ptr(d_data),
+                                                 ptr(d_mask) if d_mask is not None else None, ptr(s1), ptr(s2)))
+    else:
+        xd = np.ascontiguousarray(x)
+        if np.issubdtype(xd.dtype, np.integer):
+            xd = xd.astype(np.float64)  # "integer input is cast to float" (_scale.py:181-186)
+        if xd.dtype not in (np.float32, np.float64):
+            xd = xd.astype(np.float32)
+        is64 = int(xd.dtype == np.float64)
+        d_x = _ops._to_device(xd)
+        check(ctx.lib.sb2_dense_col_stats(ctx.handle, n, g, ptr(d_x), is64, ptr(d_mask) if d_mask is not None else None,
+                                          ptr(s1), ptr(s2)))
+    # mean_var(..., correction=1) (fast_array_utils.stats): var = (E[x^2] - E[x]^2) * n / (n - 1); g-sized, on the device
+    mean = s1 / n_sel
+    var = (s2 / n_sel - mean * mean) * (n_sel / (n_sel - 1)) if n_sel > 1 else torch.full_like(mean, float("nan"))
+    std = torch.sqrt(var)
+    std[std == 0] = 1
+    if is_sparse and not zero_center:
+        check(ctx.lib.sb2_csr_scale_cols_f32(ctx.handle, n, ptr(d_indptr), ptr(d_indices), ptr(d_data), ptr(std),
+                                             ptr(d_mask) if d_mask is not None else None, has_max, mx))
+        out = sparse.csr_matrix((_ops._to_host(d_data), xs.indices, xs.indptr), shape=xs.shape)
+    elif is_sparse:
+        warn("zero-centering a sparse array/matrix densifies it.", UserWarning)
+        d_out = torch.empty((n, g), dtype=torch.float64, device="cuda")
+        check(ctx.lib.sb2_csr_scale_dense_f64(ctx.handle, n, g, ptr(d_indptr), ptr(d_indices), ptr(d_data), ptr(mean),
+                                              ptr(std), ptr(d_mask) if d_mask is not None else None, has_max, mx,
+                                              ptr(d_out)))
+        out = _ops._to_host(d_out)
+        if mask_obs is not None:  # the reference assigns the dense block back into the sparse matrix (_scale.py:251-256)
+            out = sparse.csr_matrix(out)
+    else:
+        check(ctx.lib.sb2_dense_scale(ctx.handle, n, g, ptr(d_x), is64, ptr(mean) if zero_center else None, ptr(std),
+                                      ptr(d_mask) if d_mask is not None else None, has_max, mx))
+        out = _ops._to_host(d_x)
+    h_mean, h_std = _ops._to_host(mean, std)
+    return out, h_mean.copy(), h_std.copy()
+
+
+def scale(data, *, zero_center: bool = True, max_value: float | None = None, copy: bool = False, layer: str | None = None,
+          obsm: str | None = None, mask_obs=None):
+    """Scale data to unit variance and zero mean (signature of `scanpy.pp.scale`, _scale.py:72-147,286-327; the V1
+    preset's `zero_center=True` default)."""
+    if layer is not None or obsm is not None:
+        raise NotImplementedError("`layer`/`obsm` are not implemented in scanpy_b200.pp.scale")
+    if not zero_center and max_value is not None:
+        log_start("... be careful when using `max_value` without `zero_center`.")
+    if is_anndata_like(data):
+        adata = data.copy() if copy else data
+        names = ("mean", "std")
+        if mask_obs is not None:
+            names = (f"mean of {mask_obs}", f"std of {mask_obs}") if isinstance(mask_obs, str) else ("mean with mask", "std with mask")
+            from .pp import _check_mask
+
+            mask_obs = _check_mask(adata, mask_obs, "obs")
+        x, mean, std = _scale_array(adata.X, zero_center=zero_center, max_value=max_value, mask_obs=mask_obs)
+        adata.var[names[0]] = mean
+        adata.var[names[1]] = std
+        adata.X = x
+        return adata if copy else None
+    x = data
+    if isinstance(mask_obs, str):
+        raise ValueError("Cannot use refererence for mask without providing anndata object as argument")
+    if sparse.issparse(x) and x.format == "csc":
+        x = x.tocsr()
+    if mask_obs is not None:
+        mask_obs = np.asarray(mask_obs)
+        if mask_obs.dtype != bool:
+            raise ValueError("Mask array must be boolean.")
+        if len(mask_obs) != x.shape[0]:
+            raise ValueError("The shape of the mask do not match the data.")
+    out, _, _ = _scale_array(x, zero_center=zero_center, max_value=max_value, mask_obs=mask_obs)
+    return out

@@ -271,6 +271,21 @@ __global__ void rf_init_kernel(int32_t n, const int64_t* __restrict__ k, int32_t
   Kref[v] = k[v];
   rsize[v] = 1;
 }
+// Louvain (no refinement phase): the aggregate's super-vertices are the communities themselves
+// (community labels at an aggregated level are labels of an older level and may exceed L.n, so each community is named by
+// its smallest member, like a refined community is named by a vertex id)
+__global__ void lv_rep_kernel(int32_t n, const int32_t* __restrict__ comm, int32_t* __restrict__ rep) {
+  const int32_t v = blockIdx.x * blockDim.x + threadIdx.x;
+  if (v < n) atomicMin(&rep[comm[v]], v);
+}
+__global__ void lv_ref_kernel(int32_t n, const int32_t* __restrict__ comm, const int32_t* __restrict__ rep,
+                              int32_t* __restrict__ ref, int32_t* __restrict__ rsize) {
+  const int32_t v = blockIdx.x * blockDim.x + threadIdx.x;
+  if (v >= n) return;
+  const int32_t r = rep[comm[v]];
+  ref[v] = r;
+  atomicAdd(&rsize[r], 1);
+}
 __global__ void rf_apply_kernel(const int32_t* __restrict__ wl, int32_t n_wl, const int64_t* __restrict__ k,
                                 const int32_t* __restrict__ target, const uint8_t* __restrict__ tsingle, int32_t* __restrict__ ref,
                                 u64* __restrict__ Kref, int32_t* __restrict__ rsize, u64* __restrict__ counters) {
@@ -737,7 +752,7 @@ extern "C" int32_t sb2_modularity_csr_f32(sb2_ctx* ctx, int64_t n, const int64_t
 static int32_t leiden_core(sb2_ctx* ctx, int64_t n, const int64_t* d_indptr, const int32_t* d_indices,
                            const float* d_weights, double resolution, int32_t n_iterations, uint64_t seed,
                            int32_t* d_membership, double* h_modularity, int32_t* h_n_comms,
-                           sb2_leiden_info* info) {
+                           sb2_leiden_info* info, bool louvain = false) {
   SB2_CHECK_ARG(ctx && d_indptr && d_indices && d_weights && d_membership && h_modularity && h_n_comms, "null pointer");
   SB2_CHECK_ARG(n >= 1 && n < INT32_MAX, "n");
   SB2_CHECK_ARG(resolution >= 0.0, "resolution");
@@ -817,7 +832,16 @@ static int32_t leiden_core(sb2_ctx* ctx, int64_t n, const int64_t* d_indptr, con
         if (lev == 0 && mv == 0 && passes > 0 && prev_higher_moves == 0 && n_iterations < 0) { idle_pass = true; break; }
         ++lev;
         levels = lev;
-        SB2_TRY(refine(w, L, comm, ref, Kref, rsize));
+        if (louvain) {
+          SB2_CUDA(cudaMemsetAsync(rsize, 0, sizeof(int32_t) * L.n, st));
+          SB2_CUDA(cudaMemsetAsync(cnt, 0x7f, sizeof(int32_t) * n0, st));  // cnt doubles as the representative table here
+          lv_rep_kernel<<<gridt(L.n), 256, 0, st>>>(L.n, comm, cnt);
+          SB2_LAUNCH_CHECK(ctx);
+          lv_ref_kernel<<<gridt(L.n), 256, 0, st>>>(L.n, comm, cnt, ref, rsize);
+          SB2_LAUNCH_CHECK(ctx);
+        } else {
+          SB2_TRY(refine(w, L, comm, ref, Kref, rsize));
+        }
         pt.lap(&t_rf);
         // compact refined labels
         flag_nonempty_kernel<<<gridt(L.n), 256, 0, st>>>(L.n, rsize, flag);
@@ -937,4 +961,14 @@ extern "C" int32_t sb2_leiden_csr_f32(sb2_ctx* ctx, int64_t n, const int64_t* d_
   *h_n_comms = best_nc;
   if (info) *info = best_info;
   return SB2_OK;
+}
+
+// Louvain (Blondel et al. 2008) = the same local moving and aggregation without the refinement phase, one pass to its
+// fixed point: what `louvain.find_partition(g, RBConfigurationVertexPartition, resolution_parameter, weights, seed)` and
+// igraph's `community_multilevel` optimise (src/scanpy/tools/_louvain.py:150-176).  Same outputs as sb2_leiden_csr_f32.
+extern "C" int32_t sb2_louvain_csr_f32(sb2_ctx* ctx, int64_t n, const int64_t* d_indptr, const int32_t* d_indices,
+                                       const float* d_weights, double resolution, uint64_t seed, int32_t* d_membership,
+                                       double* h_modularity, int32_t* h_n_comms, sb2_leiden_info* info) {
+  SB2_CHECK_ARG(ctx && d_membership && h_modularity && h_n_comms, "null pointer");
+  return leiden_core(ctx, n, d_indptr, d_indices, d_weights, resolution, 1, seed, d_membership, h_modularity, h_n_comms, info, true);
 }

@@ -77,6 +77,98 @@ __global__ void reduce_copies_kernel(const double* __restrict__ src, int copies,
   dst[i] = s;
 }
 
+
+// ---- sc.pp.scale (src/scanpy/preprocessing/_scale.py:150-296) ---------------------------------------------------------
+// per-gene sum / sum of squares over the rows with mask != 0 (mask == nullptr: all rows): warp per row, fp64 REDs into
+// MV_COPIES replicated accumulators (mean_var(x[mask_obs, :], axis=0, correction=1) without materialising the subset)
+__global__ void __launch_bounds__(256)
+col_stats_rows_kernel(int64_t n, const int64_t* __restrict__ indptr, const int32_t* __restrict__ indices,
+                      const float* __restrict__ data, const uint8_t* __restrict__ mask, int g, double* __restrict__ acc) {
+  const int lane = threadIdx.x & 31;
+  const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= n || (mask && !mask[row])) return;
+  double* mine = acc + (size_t)(blockIdx.x % MV_COPIES) * 2 * g;
+  for (int64_t e = indptr[row] + lane; e < indptr[row + 1]; e += 32) {
+    const double v = (double)data[e];
+    atomicAdd(&mine[indices[e]], v);
+    atomicAdd(&mine[g + indices[e]], v * v);
+  }
+}
+// numba `scale_and_clip_csr` (_scale.py:267-283): data[j] = min(max_value, data[j] / std[col]) on the masked rows
+__global__ void __launch_bounds__(256)
+scale_cols_csr_kernel(int64_t n, const int64_t* __restrict__ indptr, const int32_t* __restrict__ indices,
+                      float* __restrict__ data, const double* __restrict__ stdv, const uint8_t* __restrict__ mask,
+                      int has_max, double max_value) {
+  const int lane = threadIdx.x & 31;
+  const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= n || (mask && !mask[row])) return;
+  for (int64_t e = indptr[row] + lane; e < indptr[row + 1]; e += 32) {
+    double v = (double)data[e] / stdv[indices[e]];
+    if (has_max) v = fmin(max_value, v);
+    data[e] = (float)v;
+  }
+}
+// zero_center=True on a CSR densifies it (`x -= mean` -> float64 dense, then / std, then clip to [-max, max]): CTA per
+// row writes the row's background (0 - mean)/std and then the stored entries; the dense row is written once (the
+// background pass skips nothing - a second write of ~5 % of the columns is cheaper than a per-column search)
+__device__ __forceinline__ double clip_sym(double v, int has_max, double mx) {
+  if (has_max) { if (v > mx) v = mx; else if (v < -mx) v = -mx; }
+  return v;
+}
+__global__ void __launch_bounds__(256)
+scale_csr_to_dense_kernel(int64_t n, int g, const int64_t* __restrict__ indptr, const int32_t* __restrict__ indices,
+                          const float* __restrict__ data, const double* __restrict__ mean, const double* __restrict__ stdv,
+                          const uint8_t* __restrict__ mask, int has_max, double max_value, double* __restrict__ out) {
+  const int64_t row = blockIdx.x;
+  double* o = out + (size_t)row * g;
+  const bool on = !mask || mask[row];   // rows outside mask_obs keep their values (`x[mask_obs, :] = scaled`)
+  for (int c = threadIdx.x; c < g; c += blockDim.x) o[c] = on ? clip_sym((0.0 - mean[c]) / stdv[c], has_max, max_value) : 0.0;
+  __syncthreads();
+  for (int64_t e = indptr[row] + threadIdx.x; e < indptr[row + 1]; e += blockDim.x) {
+    const int c = indices[e];
+    o[c] = on ? clip_sym(((double)data[e] - mean[c]) / stdv[c], has_max, max_value) : (double)data[e];
+  }
+}
+// dense input: column sums over the masked rows; a CTA owns DS_ROWS rows, thread t the columns t, t+256, ...
+constexpr int DS_ROWS = 64;
+template <typename T>
+__global__ void __launch_bounds__(256)
+dense_col_stats_kernel(int64_t n, int g, const T* __restrict__ x, const uint8_t* __restrict__ mask, double* __restrict__ acc) {
+  const int64_t r0 = (int64_t)blockIdx.x * DS_ROWS;
+  const int64_t r1 = r0 + DS_ROWS < n ? r0 + DS_ROWS : n;
+  double* mine = acc + (size_t)(blockIdx.x % MV_COPIES) * 2 * g;
+  for (int c = threadIdx.x; c < g; c += blockDim.x) {
+    double s = 0.0, q = 0.0;
+    for (int64_t r = r0; r < r1; ++r) {
+      if (mask && !mask[r]) continue;
+      const double v = (double)x[(size_t)r * g + c];
+      s += v;
+      q += v * v;
+    }
+    atomicAdd(&mine[c], s);
+    atomicAdd(&mine[g + c], q);
+  }
+}
+// dense input, in place: `x -= mean` (rounded to T), `x /= std` (rounded to T), clip_array (_scale.py:52-69): the lower
+// bound only applies with zero_center
+template <typename T>
+__global__ void dense_scale_kernel(int64_t n, int g, T* __restrict__ x, const double* __restrict__ mean,
+                                   const double* __restrict__ stdv, const uint8_t* __restrict__ mask, int has_max, double max_value) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n * g) return;
+  const int64_t r = i / g;
+  const int c = (int)(i - r * g);
+  if (mask && !mask[r]) return;
+  T v = x[i];
+  if (mean) v = (T)((double)v - mean[c]);
+  v = (T)((double)v / stdv[c]);
+  if (has_max) {
+    const T mx = (T)max_value;
+    if (v > mx) v = mx; else if (mean && v < -mx) v = -mx;
+  }
+  x[i] = v;
+}
+
 inline unsigned gridw(int64_t n) { return (unsigned)ceil_div64(n, 8); }
 
 }  // namespace
@@ -144,6 +236,83 @@ int32_t sb2_csr_col_sums_f32(sb2_ctx* ctx, int64_t nnz, int32_t g, const int32_t
   SB2_LAUNCH_CHECK(ctx);
   SB2_CUDA(cudaMemcpyAsync(d_sum, both, sizeof(double) * g, cudaMemcpyDeviceToDevice, ctx->stream));
   SB2_CUDA(cudaMemcpyAsync(d_sumsq, both + g, sizeof(double) * g, cudaMemcpyDeviceToDevice, ctx->stream));
+  return SB2_OK;
+}
+
+static int32_t finish_col_stats(sb2_ctx* ctx, const double* acc, double* both, int32_t g, double* d_sum, double* d_sumsq) {
+  reduce_copies_kernel<<<(unsigned)ceil_div64(2 * g, 256), 256, 0, ctx->stream>>>(acc, MV_COPIES, 2 * (int64_t)g, both);
+  SB2_LAUNCH_CHECK(ctx);
+  SB2_CUDA(cudaMemcpyAsync(d_sum, both, sizeof(double) * g, cudaMemcpyDeviceToDevice, ctx->stream));
+  SB2_CUDA(cudaMemcpyAsync(d_sumsq, both + g, sizeof(double) * g, cudaMemcpyDeviceToDevice, ctx->stream));
+  return SB2_OK;
+}
+
+int32_t sb2_csr_col_stats_rows_f32(sb2_ctx* ctx, int64_t n, int32_t g, const int64_t* d_indptr, const int32_t* d_indices,
+                                   const float* d_data, const uint8_t* d_mask, double* d_sum, double* d_sumsq) {
+  SB2_CHECK_ARG(ctx && d_indptr && d_sum && d_sumsq && g >= 1, "null pointer");
+  SB2_CUDA(cudaSetDevice(ctx->device));
+  ScratchScope scr(ctx);
+  double *acc, *both;
+  SB2_TRY(scr.alloc(&acc, (size_t)MV_COPIES * 2 * g));
+  SB2_TRY(scr.alloc(&both, (size_t)2 * g));
+  SB2_CUDA(cudaMemsetAsync(acc, 0, sizeof(double) * MV_COPIES * 2 * g, ctx->stream));
+  if (n > 0) {
+    col_stats_rows_kernel<<<gridw(n), 256, 0, ctx->stream>>>(n, d_indptr, d_indices, d_data, d_mask, g, acc);
+    SB2_LAUNCH_CHECK(ctx);
+  }
+  return finish_col_stats(ctx, acc, both, g, d_sum, d_sumsq);
+}
+
+int32_t sb2_csr_scale_cols_f32(sb2_ctx* ctx, int64_t n, const int64_t* d_indptr, const int32_t* d_indices, float* d_data,
+                               const double* d_std, const uint8_t* d_mask, int32_t has_max, double max_value) {
+  SB2_CHECK_ARG(ctx && d_indptr && d_std, "null pointer");
+  SB2_CUDA(cudaSetDevice(ctx->device));
+  if (n == 0) return SB2_OK;
+  scale_cols_csr_kernel<<<gridw(n), 256, 0, ctx->stream>>>(n, d_indptr, d_indices, d_data, d_std, d_mask, has_max, max_value);
+  SB2_LAUNCH_CHECK(ctx);
+  return SB2_OK;
+}
+
+int32_t sb2_csr_scale_dense_f64(sb2_ctx* ctx, int64_t n, int32_t g, const int64_t* d_indptr, const int32_t* d_indices,
+                                const float* d_data, const double* d_mean, const double* d_std, const uint8_t* d_mask,
+                                int32_t has_max, double max_value, double* d_out) {
+  SB2_CHECK_ARG(ctx && d_indptr && d_mean && d_std && d_out && g >= 1, "null pointer");
+  SB2_CHECK_ARG(n < INT32_MAX, "n");
+  SB2_CUDA(cudaSetDevice(ctx->device));
+  if (n == 0) return SB2_OK;
+  scale_csr_to_dense_kernel<<<(unsigned)n, 256, 0, ctx->stream>>>(n, g, d_indptr, d_indices, d_data, d_mean, d_std, d_mask,
+                                                                 has_max, max_value, d_out);
+  SB2_LAUNCH_CHECK(ctx);
+  return SB2_OK;
+}
+
+int32_t sb2_dense_col_stats(sb2_ctx* ctx, int64_t n, int32_t g, const void* d_x, int32_t is_f64, const uint8_t* d_mask,
+                            double* d_sum, double* d_sumsq) {
+  SB2_CHECK_ARG(ctx && d_x && d_sum && d_sumsq && g >= 1, "null pointer");
+  SB2_CUDA(cudaSetDevice(ctx->device));
+  ScratchScope scr(ctx);
+  double *acc, *both;
+  SB2_TRY(scr.alloc(&acc, (size_t)MV_COPIES * 2 * g));
+  SB2_TRY(scr.alloc(&both, (size_t)2 * g));
+  SB2_CUDA(cudaMemsetAsync(acc, 0, sizeof(double) * MV_COPIES * 2 * g, ctx->stream));
+  if (n > 0) {
+    const unsigned grid = (unsigned)ceil_div64(n, DS_ROWS);
+    if (is_f64) dense_col_stats_kernel<double><<<grid, 256, 0, ctx->stream>>>(n, g, (const double*)d_x, d_mask, acc);
+    else dense_col_stats_kernel<float><<<grid, 256, 0, ctx->stream>>>(n, g, (const float*)d_x, d_mask, acc);
+    SB2_LAUNCH_CHECK(ctx);
+  }
+  return finish_col_stats(ctx, acc, both, g, d_sum, d_sumsq);
+}
+
+int32_t sb2_dense_scale(sb2_ctx* ctx, int64_t n, int32_t g, void* d_x, int32_t is_f64, const double* d_mean,
+                        const double* d_std, const uint8_t* d_mask, int32_t has_max, double max_value) {
+  SB2_CHECK_ARG(ctx && d_x && d_std && g >= 1, "null pointer");
+  SB2_CUDA(cudaSetDevice(ctx->device));
+  if (n == 0) return SB2_OK;
+  const unsigned grid = (unsigned)ceil_div64(n * g, 256);
+  if (is_f64) dense_scale_kernel<double><<<grid, 256, 0, ctx->stream>>>(n, g, (double*)d_x, d_mean, d_std, d_mask, has_max, max_value);
+  else dense_scale_kernel<float><<<grid, 256, 0, ctx->stream>>>(n, g, (float*)d_x, d_mean, d_std, d_mask, has_max, max_value);
+  SB2_LAUNCH_CHECK(ctx);
   return SB2_OK;
 }
 

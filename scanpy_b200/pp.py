@@ -15,7 +15,7 @@ import numpy as np
 from scipy import sparse
 
 from . import _ops
-from ._preprocess import highly_variable_genes, log1p, normalize_total  # noqa: F401  
+from ._preprocess import highly_variable_genes, log1p, normalize_total, scale  # noqa: F401  
 from ._compat import (MiniAnnData, accepts_legacy_random_state, as_csr_f32, is_anndata_like, log_done, log_start,
                       meta_random_state, seed_from_rng, settings, warn)
 

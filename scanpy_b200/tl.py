@@ -7,13 +7,14 @@ objective both reference back-ends optimise for scanpy's defaults (RB configurat
 """
 from __future__ import annotations
 
-from typing import Sequence
+from types import MappingProxyType
+from typing import Any, Mapping, Sequence
 
 import numpy as np
 import pandas as pd
 
 from . import _ops
-from ._compat import accepts_legacy_random_state, log_done, log_start, meta_random_state, seed_from_rng
+from ._compat import accepts_legacy_random_state, log_done, log_start, meta_random_state, seed_from_rng, warn
 
 
 def _validate_flavor(flavor, *, partition_type, directed) -> str:
@@ -112,6 +113,62 @@ def leiden(adata, resolution: float = 1, *, restrict_to=None, rng=None, key_adde
     adata.uns[key_added] = {}
     adata.uns[key_added]["params"] = dict(resolution=resolution, n_iterations=n_iterations, **meta_rs)
     adata.uns[key_added]["modularity"] = modularity
+    log_done(start, f"found {len(cats)} clusters and added {key_added!r}, the cluster labels (adata.obs, categorical)")
+    return adata if copy else None
+
+
+def louvain(adata, resolution: float | None = None, *, random_state=0, restrict_to=None, key_added: str = "louvain",
+            adjacency=None, flavor: str = "vtraag", directed: bool = True, use_weights: bool = False, partition_type=None,
+            partition_kwargs: Mapping[str, Any] = MappingProxyType({}), neighbors_key: str | None = None,
+            obsp: str | None = None, copy: bool = False):
+    """Louvain clustering (signature of `scanpy.tl.louvain`, tools/_louvain.py:49-213).
+
+    Both reference flavors maximise (RB-configuration) modularity by local moving + aggregation; the device kernel
+    (sb2_louvain_csr_f32) optimises that objective on the SYMMETRIC graph: `directed=True` (the vtraag default) only
+    changes how the reference counts the two arcs of each symmetric pair, which for a symmetric adjacency is the same
+    objective up to the factor 2 in the edge total.  flavor='igraph' ignores `resolution` like the reference."""
+    if flavor not in ("vtraag", "igraph"):
+        if flavor == "taynaud":
+            raise NotImplementedError("flavor='taynaud' (deprecated python-louvain) is not implemented in scanpy_b200")
+        raise ValueError('`flavor` needs to be "vtraag" or "igraph" or "taynaud".')
+    if flavor != "vtraag" and partition_type is not None:
+        raise ValueError('`partition_type` is only a valid argument when `flavour` is "vtraag"')
+    if partition_type is not None or dict(partition_kwargs):
+        raise NotImplementedError("custom `partition_type` / `partition_kwargs` are not implemented in scanpy_b200 "
+                                  "(RBConfigurationVertexPartition only)")
+    start = log_start("running Louvain clustering")
+    adata = adata.copy() if copy else adata
+    if adjacency is None:
+        adjacency = _choose_graph(adata, obsp, neighbors_key)
+    restrict_indices = restrict_key = restrict_categories = None
+    if restrict_to is not None:
+        restrict_key, restrict_categories = restrict_to
+        adjacency, restrict_indices = _restrict_adjacency(adata, restrict_key, restrict_categories=restrict_categories,
+                                                          adjacency=adjacency)
+    if flavor == "igraph" and resolution is not None:
+        warn('`resolution` parameter has no effect for flavor "igraph"')
+    adj = adjacency.tocsr()
+    if adj.dtype != np.float32:
+        adj = adj.astype(np.float32)
+    if not use_weights:
+        adj = adj.copy()
+        adj.data[:] = 1.0
+    gamma = 1.0 if (resolution is None or flavor == "igraph") else float(resolution)
+    seed = 0 if random_state is None else int(random_state)
+    groups, _q, _info = _ops.louvain(adj, resolution=gamma, seed=seed)
+    if restrict_to is not None:
+        if key_added == "louvain":
+            key_added += "_R"
+        groups = _rename_groups(adata, restrict_key, restrict_categories=restrict_categories,
+                                restrict_indices=restrict_indices, groups=groups)
+        cats = sorted(map(str, np.unique(groups)), key=_natkey)
+        adata.obs[key_added] = pd.Categorical(values=np.asarray(groups).astype("U"), categories=cats)
+    else:
+        n_groups = int(groups.max()) + 1 if len(groups) else 0
+        cats = [str(c) for c in range(n_groups)]
+        adata.obs[key_added] = pd.Categorical.from_codes(groups.astype(np.int32), categories=cats)
+    adata.uns[key_added] = {}
+    adata.uns[key_added]["params"] = dict(resolution=resolution, random_state=random_state)
     log_done(start, f"found {len(cats)} clusters and added {key_added!r}, the cluster labels (adata.obs, categorical)")
     return adata if copy else None
 

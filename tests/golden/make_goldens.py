@@ -100,6 +100,10 @@ def main() -> None:
         {"X", "n_neighbors", "distances_euclidean", "distances_euclidean_all", "connectivities_umap",
          "connectivities_gauss_knn", "connectivities_jaccard"},
     )
+    sc_names = {"X_original", "X_scaled_original", "X_centered_original", "X_scaled_original_clipped", "X_for_mask",
+                "X_scaled_for_mask", "X_centered_for_mask", "X_scaled_for_mask_clipped"}
+    sc_l = literals_from(REF / "tests/test_scaling.py", sc_names)  # tests/test_scaling.py:13-69
+    np.savez(OUT / "reference_scaling_literals.npz", **{k: v.astype(np.float64) for k, v in sc_l.items()})
     np.savez(OUT / "reference_test_literals.npz",
              A_list=pca_l["A_list"].astype(np.float64), A_pca=pca_l["A_pca"], A_svd=pca_l["A_svd"],
              X4=nb_l["X"].astype(np.float64), n_neighbors4=np.int64(nb_l["n_neighbors"]),

@@ -158,3 +158,30 @@ def test_hvg_seurat_oracle_matches_seurat_csv():
     np.testing.assert_array_equal(df["highly_variable"].to_numpy(), f["highly_variable"])
     for k in ("means", "dispersions", "dispersions_norm"):
         np.testing.assert_allclose(df[k].to_numpy(), f[k], rtol=2e-5, atol=2e-5)
+
+
+# ------------------------------------------------------------------------------------------ pp.scale oracle
+@pytest.mark.parametrize("sp", [False, True])
+@pytest.mark.parametrize("zero_center", [True, False])
+@pytest.mark.parametrize("masked", [False, True])
+def test_scale_oracle_reproduces_reference_goldens(sp, zero_center, masked):
+    """oracle.preprocess.scale vs the literals of tests/test_scaling.py:13-69 (same matrix as :72-116)."""
+    from scipy import sparse
+
+    from oracle import preprocess as opre
+
+    from conftest import GOLDEN
+
+    L = np.load(GOLDEN / "reference_scaling_literals.npz")
+    if sp and masked and zero_center:
+        pytest.skip("the reference assigns a dense block into a sparse matrix there; covered on the GPU side")
+    x0 = (L["X_for_mask"] if masked else L["X_original"]).astype(np.float32)
+    mask = np.array((0, 0, 1, 1, 1, 0, 0), dtype=bool) if masked else None
+    expected = (L["X_centered_for_mask"] if zero_center else L["X_scaled_for_mask"]) if masked else (
+        L["X_centered_original"] if zero_center else L["X_scaled_original"])
+    out, mean, std = opre.scale(sparse.csr_matrix(x0) if sp else x0, zero_center=zero_center, mask_obs=mask)
+    out = out.toarray() if sparse.issparse(out) else out
+    assert np.allclose(out, expected)
+    assert np.allclose(std, [1, 1, 2, 1])  # "gene std 1,0,2,0" with the zeros replaced by 1
+    clipped, _, _ = opre.scale(x0, zero_center=False, max_value=1, mask_obs=mask)
+    assert np.allclose(clipped, L["X_scaled_for_mask_clipped"] if masked else L["X_scaled_original_clipped"])
