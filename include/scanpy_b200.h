@@ -129,6 +129,25 @@ int32_t sb2_spmm_csr_t(sb2_ctx* ctx, int64_t n, int32_t g, int32_t l, const int6
 int32_t sb2_csr_gram(sb2_ctx* ctx, int64_t n, int32_t g, const int64_t* d_indptr, const int32_t* d_indices,
                      const float* d_data, double* d_gram);
 
+/* ---- out-of-core / chunked PCA: sc.pp.pca(chunked=True) (src/scanpy/preprocessing/_pca/__init__.py:245-271) ----
+ * The reference streams row chunks through sklearn.decomposition.IncrementalPCA and asserts the result equals the full PCA
+ * (tests/test_pca.py:357-386).  Here the chunks stream through the exact Gram route: device memory = one chunk + 2 g^2
+ * doubles, independent of n.
+ *   pass 1: sb2_pca_stream_accumulate_f32 adds the chunk's column sums / sums of squares into d_stats fp64 [2g] and its
+ *           X^T X into d_gram fp64 [g x g] (caller zero-fills both before the first chunk);
+ *   solve : sb2_pca_stream_solve_f32 -> d_components [k x g], h_var, h_var_ratio, h_mean as sb2_pca_csr_f32, plus the
+ *           projection operator d_proj fp32 [g x 128] (first g * *h_l entries used), d_shift fp32 [128], *h_l (32/64/128);
+ *   pass 2: sb2_pca_stream_project_f32 -> d_x_pca [n_chunk x k] = X_chunk U - mu^T U. */
+int32_t sb2_pca_stream_accumulate_f32(sb2_ctx* ctx, int64_t n_chunk, int32_t g, const int64_t* d_indptr,
+                                      const int32_t* d_indices, const float* d_data, double* d_stats, double* d_gram);
+int32_t sb2_pca_stream_solve_f32(sb2_ctx* ctx, int64_t n_total, int32_t g, const double* d_stats, const double* d_gram,
+                                 int32_t k, int32_t max_iter, double tol, uint64_t seed, float* d_components, double* h_var,
+                                 double* h_var_ratio, double* h_mean, float* d_proj, float* d_shift, int32_t* h_l,
+                                 sb2_pca_info* info);
+int32_t sb2_pca_stream_project_f32(sb2_ctx* ctx, int64_t n_chunk, int32_t g, const int64_t* d_indptr,
+                                   const int32_t* d_indices, const float* d_data, int32_t k, int32_t l, const float* d_proj,
+                                   const float* d_shift, float* d_x_pca);
+
 /* ---- exact brute-force kNN (euclidean) -----------------------------------------------------
  * points: d_x [n_points x d] float32 row-major.  Queries are rows [q0, q0+n_query) of the same
  * array (q0 % 128 == 0 unless n_query == n_points).  k includes the query itself: column 0 of
@@ -200,6 +219,44 @@ int32_t sb2_log1p_f32(sb2_ctx* ctx, int64_t nnz, float* d_data, double base);
 int32_t sb2_csr_col_sums_f32(sb2_ctx* ctx, int64_t nnz, int32_t g, const int32_t* d_indices, const float* d_data,
                              int32_t apply_expm1, double log_scale, double* d_sum, double* d_sumsq);
 
+
+/* ---- extreme eigenpairs of diag(s) A diag(s), A symmetric fp32 CSR (csrc/eigs.cu: thick-restart Lanczos, fp64) ----
+ * Replaces `scipy.sparse.linalg.eigsh(matrix.astype(float64), k=n_comps, which='LM', v0=...)` in
+ * Neighbors.compute_eigen (src/scanpy/neighbors/__init__.py:832-884; sc.tl.diffmap) and the eigsh of umap's spectral
+ * initialisation (sc.tl.umap).  d_scale may be NULL (s = 1).  which: 0 largest algebraic, 1 largest magnitude, 2 smallest
+ * algebraic.  ncv <= 0 / tol <= 0 / max_restarts <= 0 pick defaults (max(2 nev + 16, 40), 1e-10, 400).  h_evals ascending
+ * like eigsh; d_evecs fp64 [nev x n], row e = unit eigenvector of h_evals[e] (sign arbitrary, as with ARPACK). */
+typedef struct sb2_eigs_info {
+  int32_t restarts, matvecs, n_converged, reserved;
+  double max_residual;
+} sb2_eigs_info;
+int32_t sb2_eigsh_csr_scaled(sb2_ctx* ctx, int64_t n, const int64_t* d_indptr, const int32_t* d_indices,
+                             const float* d_weights, const double* d_scale, int32_t nev, int32_t which, int32_t ncv,
+                             double tol, int32_t max_restarts, const double* d_v0, double* h_evals, double* d_evecs,
+                             sb2_eigs_info* info);
+/* d_scale fp64[n] with T_sym = diag(d_scale) W diag(d_scale): the symmetrised transition matrix of
+ * Neighbors.compute_transitions (src/scanpy/neighbors/__init__.py:791-830; density_normalize as there). */
+int32_t sb2_transition_scale_f64(sb2_ctx* ctx, int64_t n, const int64_t* d_indptr, const int32_t* d_indices,
+                                 const float* d_weights, int32_t density_normalize, double* d_scale);
+
+/* ---- sc.tl.umap layout (csrc/umap.cu) ----
+ * Replaces `umap.umap_.simplicial_set_embedding` as called at src/scanpy/tools/_umap.py:196-215.
+ * sb2_umap_spectral_init_f32: init='spectral' (eigenvectors 2..dim+1 of D^-1/2 A D^-1/2, expanded to max|x| = 10, N(0,1e-4)
+ *   jitter) into d_init fp32 [n x dim].
+ * sb2_umap_layout_f32: d_embedding fp32 [n x dim] holds the initialisation on entry (rescaled to [0,10]^dim first, like the
+ *   reference) and the optimised layout on return; graph = symmetric connectivities CSR (not modified); a, b from
+ *   find_ab_params(spread, min_dist); deterministic in (graph, init, seed). */
+int32_t sb2_umap_spectral_init_f32(sb2_ctx* ctx, int64_t n, const int64_t* d_indptr, const int32_t* d_indices,
+                                   const float* d_weights, int32_t dim, uint64_t seed, float* d_init);
+int32_t sb2_umap_layout_f32(sb2_ctx* ctx, int64_t n, const int64_t* d_indptr, const int32_t* d_indices, const float* d_weights,
+                            int32_t dim, int32_t n_epochs, double a, double b, double gamma, double initial_alpha,
+                            int32_t negative_sample_rate, uint64_t seed, float* d_embedding);
+
+/* ---- sc.tl.paga aggregation: d_counts int64 [G x G], counts[gi*G + gj] = stored arcs i -> j with
+ * d_group[i] = gi, d_group[j] = gj.  Replaces igraph's VertexClustering.cluster_graph / subgraph(i).ecount() at
+ * src/scanpy/tools/_paga.py:177-208 (inner-cluster edge counts are the diagonal). */
+int32_t sb2_group_arc_counts(sb2_ctx* ctx, int64_t n, const int64_t* d_indptr, const int32_t* d_indices,
+                             const int32_t* d_group, int32_t n_groups, int64_t* d_counts);
 
 /* ---- sc.pp.scale (SURVEY.md 8f row f2 tail; src/scanpy/preprocessing/_scale.py:150-296) ----
  * sb2_csr_col_stats_rows_f32 <- mean_var(x[mask_obs, :], axis=0, correction=1): per-gene sum / sum of squares (fp64) over

@@ -42,6 +42,11 @@ class KnnInfo(ctypes.Structure):
                 ("pass1_issued_flops", c_double), ("pass1_tensor", c_int32), ("n_resweep", c_int64)]
 
 
+class EigsInfo(ctypes.Structure):
+    _fields_ = [("restarts", c_int32), ("matvecs", c_int32), ("n_converged", c_int32), ("reserved", c_int32),
+                ("max_residual", c_double)]
+
+
 class LeidenInfo(ctypes.Structure):
     _fields_ = [("passes", c_int32), ("levels", c_int32), ("moves", c_int64)]
 
@@ -62,6 +67,12 @@ SIGNATURES = {
     "sb2_pca_csr_f32": (c_int32, [c_void_p, c_int64, c_int64, c_int32, c_void_p, c_void_p, c_void_p, c_int32,
                                   c_int32, c_int32, c_double, c_uint64, c_void_p, c_void_p, c_void_p, c_void_p,
                                   c_void_p, POINTER(PcaInfo)]),
+    "sb2_pca_stream_accumulate_f32": (c_int32, [c_void_p, c_int64, c_int32, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "sb2_pca_stream_solve_f32": (c_int32, [c_void_p, c_int64, c_int32, c_void_p, c_void_p, c_int32, c_int32, c_double,
+                                           c_uint64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                           POINTER(c_int32), POINTER(PcaInfo)]),
+    "sb2_pca_stream_project_f32": (c_int32, [c_void_p, c_int64, c_int32, c_void_p, c_void_p, c_void_p, c_int32, c_int32,
+                                             c_void_p, c_void_p, c_void_p]),
     "sb2_csr_col_stats": (c_int32, [c_void_p, c_int64, c_int32, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "sb2_spmm_csr": (c_int32, [c_void_p, c_int64, c_int32, c_int32, c_void_p, c_void_p, c_void_p, c_void_p,
                                c_void_p, c_void_p]),
@@ -81,6 +92,13 @@ SIGNATURES = {
                                      c_void_p, POINTER(c_double), POINTER(c_int32), POINTER(LeidenInfo)]),
     "sb2_modularity_csr_f32": (c_int32, [c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_double, c_void_p,
                                          POINTER(c_double)]),
+    "sb2_eigsh_csr_scaled": (c_int32, [c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32,
+                                       c_double, c_int32, c_void_p, c_void_p, c_void_p, POINTER(EigsInfo)]),
+    "sb2_transition_scale_f64": (c_int32, [c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_int32, c_void_p]),
+    "sb2_umap_spectral_init_f32": (c_int32, [c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_int32, c_uint64, c_void_p]),
+    "sb2_umap_layout_f32": (c_int32, [c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_double, c_double,
+                                      c_double, c_double, c_int32, c_uint64, c_void_p]),
+    "sb2_group_arc_counts": (c_int32, [c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_int32, c_void_p]),
     "sb2_louvain_csr_f32": (c_int32, [c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_double, c_uint64,
                                       c_void_p, POINTER(c_double), POINTER(c_int32), POINTER(LeidenInfo)]),
     "sb2_csr_col_stats_rows_f32": (c_int32, [c_void_p, c_int64, c_int32, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,

@@ -12,7 +12,7 @@ from ctypes import byref, c_double, c_int32, c_int64
 import numpy as np
 
 from . import _abi
-from ._abi import KnnInfo, LeidenInfo, PcaInfo, check, ptr
+from ._abi import EigsInfo, KnnInfo, LeidenInfo, PcaInfo, check, ptr
 
 
 def _torch():
@@ -140,6 +140,47 @@ def pca_csr(x, n_comps: int, *, solver: int = 0, max_iter: int = 0, tol: float =
     out["X_pca"], out["components"] = _to_host(out["X_pca"], out["components"])
     RESIDENT.put(out["X_pca"], d_x_pca)
     return out
+
+
+def pca_csr_chunked(x, n_comps: int, *, chunk_size: int, seed: int = 0, ctx=None):
+    """Out-of-core PCA of a host scipy CSR: the rows stream through the device `chunk_size` at a time (two passes: Gram
+    accumulation, projection); device memory holds one chunk + the g x g Gram matrix.  Same outputs as `pca_csr`."""
+    torch = _torch()
+    ctx = ctx or _abi.default_context()
+    n, g = x.shape
+    chunk_size = max(1, int(chunk_size))
+    stats = torch.zeros(2 * g, dtype=torch.float64, device="cuda")
+    gram = torch.zeros((g, g), dtype=torch.float64, device="cuda")
+
+    def chunks():
+        for r0 in range(0, n, chunk_size):
+            r1 = min(n, r0 + chunk_size)
+            lo, hi = int(x.indptr[r0]), int(x.indptr[r1])
+            indptr = np.asarray(x.indptr[r0:r1 + 1], dtype=np.int64) - lo
+            yield r0, r1, _to_device(indptr), _to_device(np.asarray(x.indices[lo:hi], dtype=np.int32)), \
+                _to_device(np.asarray(x.data[lo:hi], dtype=np.float32))
+
+    for r0, r1, dp, di, dd in chunks():
+        check(ctx.lib.sb2_pca_stream_accumulate_f32(ctx.handle, r1 - r0, g, ptr(dp), ptr(di), ptr(dd), ptr(stats), ptr(gram)))
+    comps = torch.empty((n_comps, g), dtype=torch.float32, device="cuda")
+    proj = torch.empty(g * 128, dtype=torch.float32, device="cuda")
+    shift = torch.empty(128, dtype=torch.float32, device="cuda")
+    var = np.empty(n_comps, np.float64)
+    ratio = np.empty(n_comps, np.float64)
+    mean = np.empty(g, np.float64)
+    l = c_int32()
+    info = PcaInfo()
+    check(ctx.lib.sb2_pca_stream_solve_f32(ctx.handle, n, g, ptr(stats), ptr(gram), n_comps, 0, 0.0, seed, ptr(comps), ptr(var),
+                                           ptr(ratio), ptr(mean), ptr(proj), ptr(shift), byref(l), byref(info)))
+    x_pca = np.empty((n, n_comps), np.float32)
+    for r0, r1, dp, di, dd in chunks():
+        part = torch.empty((r1 - r0, n_comps), dtype=torch.float32, device="cuda")
+        check(ctx.lib.sb2_pca_stream_project_f32(ctx.handle, r1 - r0, g, ptr(dp), ptr(di), ptr(dd), n_comps, l.value, ptr(proj),
+                                                 ptr(shift), ptr(part)))
+        x_pca[r0:r1] = _to_host(part)
+    return dict(X_pca=x_pca, components=_to_host(comps), variance=var, variance_ratio=ratio, mean=mean,
+                iterations=info.iterations, converged=bool(info.converged), max_rel_residual=info.max_rel_residual,
+                total_var=info.total_var)
 
 
 # ------------------------------------------------------------------------------------------ kNN
@@ -298,3 +339,44 @@ def modularity(adj, membership, *, resolution: float = 1.0, ctx=None) -> float:
     check(ctx.lib.sb2_modularity_csr_f32(ctx.handle, adj.shape[0], ptr(d_indptr), ptr(d_indices), ptr(d_w),
                                          float(resolution), ptr(d_m), byref(q)))
     return q.value
+
+
+# ------------------------------------------------------------------------------------------ eigsh / diffmap / umap
+def eigsh_scaled_device(ctx, d_indptr, d_indices, d_w, n: int, nev: int, *, d_scale=None, which: str = "LM", v0=None,
+                        ncv: int = 0, tol: float = 0.0, max_restarts: int = 0):
+    """Extreme eigenpairs of diag(s) A diag(s) on the device -> (evals float64[nev] ascending, evecs CUDA float64 [nev, n], info)."""
+    torch = _torch()
+    code = {"LA": 0, "LM": 1, "SA": 2}[which]
+    if v0 is None:
+        v0 = np.random.default_rng(0).standard_normal(n)
+    d_v0 = _to_device(np.ascontiguousarray(v0, dtype=np.float64))
+    evals = np.empty(nev, np.float64)
+    evecs = torch.empty((nev, n), dtype=torch.float64, device="cuda")
+    info = EigsInfo()
+    check(ctx.lib.sb2_eigsh_csr_scaled(ctx.handle, n, ptr(d_indptr), ptr(d_indices), ptr(d_w),
+                                       ptr(d_scale) if d_scale is not None else None, int(nev), code, int(ncv), float(tol),
+                                       int(max_restarts), ptr(d_v0), evals.ctypes.data, ptr(evecs), byref(info)))
+    return evals, evecs, dict(restarts=info.restarts, matvecs=info.matvecs, n_converged=info.n_converged,
+                              max_residual=info.max_residual)
+
+
+def umap_layout(adj, *, n_components: int, n_epochs: int, a: float, b: float, gamma: float, initial_alpha: float,
+                negative_sample_rate: int, seed: int, init, ctx=None):
+    """`simplicial_set_embedding` on a symmetric scipy CSR graph -> float32 [n, n_components].
+    init: 'spectral' or a float32 [n, n_components] array."""
+    torch = _torch()
+    ctx = ctx or _abi.default_context()
+    adj = adj.tocsr()
+    n = adj.shape[0]
+    d_indptr, d_indices, d_w = csr_to_device(adj)
+    if isinstance(init, str):
+        assert init == "spectral"
+        emb = torch.empty((n, n_components), dtype=torch.float32, device="cuda")
+        check(ctx.lib.sb2_umap_spectral_init_f32(ctx.handle, n, ptr(d_indptr), ptr(d_indices), ptr(d_w), int(n_components),
+                                                 int(seed), ptr(emb)))
+    else:
+        emb = _to_device(np.ascontiguousarray(init, dtype=np.float32))
+    check(ctx.lib.sb2_umap_layout_f32(ctx.handle, n, ptr(d_indptr), ptr(d_indices), ptr(d_w), int(n_components), int(n_epochs),
+                                      float(a), float(b), float(gamma), float(initial_alpha), int(negative_sample_rate),
+                                      int(seed), ptr(emb)))
+    return _to_host(emb)

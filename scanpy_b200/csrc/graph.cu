@@ -374,3 +374,44 @@ extern "C" int32_t sb2_fuzzy_simplicial_set_f32(sb2_ctx* ctx, int64_t n, int32_t
                            h_nnz);
 }
 
+
+// ---- sc.tl.paga aggregation ----------------------------------------------------------------------
+// counts[gi * G + gj] = number of stored arcs i -> j with group[i] = gi, group[j] = gj: what igraph's
+// `VertexClustering.cluster_graph(combine_edges="sum")` + `subgraph(i).ecount()` give PAGA on the all-ones distances graph
+// (src/scanpy/tools/_paga.py:177-208).  Warp per row: the lanes' target groups are merged with MATCH.ANY, so a row whose
+// neighbours sit in one or two groups issues one or two atomics.
+namespace {
+__global__ void __launch_bounds__(256)
+group_arc_counts_kernel(int64_t n, const int64_t* __restrict__ indptr, const int32_t* __restrict__ indices,
+                        const int32_t* __restrict__ group, int G, unsigned long long* __restrict__ counts) {
+  const int lane = threadIdx.x & 31;
+  const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= n) return;
+  const int gi = group[row];
+  const int64_t e0 = indptr[row], e1 = indptr[row + 1];
+  for (int64_t base = e0; base < e1; base += 32) {
+    const int64_t e = base + lane;
+    const bool on = e < e1;
+    const int gj = on ? group[indices[e]] : -1;
+    const unsigned act = __ballot_sync(0xffffffffu, on);
+    if (on) {
+      const unsigned same = __match_any_sync(act, gj);
+      if ((int)(__ffs(same) - 1) == lane && gi >= 0 && gi < G && gj >= 0 && gj < G)
+        atomicAdd(&counts[(size_t)gi * G + gj], (unsigned long long)__popc(same));
+    }
+  }
+}
+}  // namespace
+
+extern "C" int32_t sb2_group_arc_counts(sb2_ctx* ctx, int64_t n, const int64_t* d_indptr, const int32_t* d_indices,
+                                        const int32_t* d_group, int32_t n_groups, int64_t* d_counts) {
+  SB2_CHECK_ARG(ctx && d_indptr && d_indices && d_group && d_counts, "null pointer");
+  SB2_CHECK_ARG(n_groups >= 1 && n_groups <= 46340, "n_groups");
+  SB2_CUDA(cudaSetDevice(ctx->device));
+  SB2_CUDA(cudaMemsetAsync(d_counts, 0, sizeof(int64_t) * (size_t)n_groups * n_groups, ctx->stream));
+  if (n == 0) return SB2_OK;
+  group_arc_counts_kernel<<<(unsigned)ceil_div64(n, 8), 256, 0, ctx->stream>>>(n, d_indptr, d_indices, d_group, n_groups,
+                                                                            reinterpret_cast<unsigned long long*>(d_counts));
+  SB2_LAUNCH_CHECK(ctx);
+  return SB2_OK;
+}

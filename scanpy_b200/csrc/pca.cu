@@ -787,11 +787,19 @@ int32_t sb2_csr_gram(sb2_ctx* ctx, int64_t n, int32_t g, const int64_t* d_indptr
   return SB2_OK;
 }
 
-int32_t sb2_pca_csr_f32(sb2_ctx* ctx, int64_t n, int64_t n_total, int32_t g, const int64_t* d_indptr,
+// pre_stats / pre_gram (both or neither): column sums [g] + sums of squares [g] and the Gram matrix X^T X [g x g] of ALL
+// rows, accumulated by the caller (sb2_pca_stream_accumulate_f32); the CSR arguments are then unused and nothing is
+// projected.  d_proj_out [g x l] / d_shift_out [l] / *l_out: the float32 projection operator (sign-fixed Ritz vectors and
+// mu^T U) for sb2_pca_stream_project_f32.
+static int32_t pca_core(sb2_ctx* ctx, int64_t n, int64_t n_total, int32_t g, const int64_t* d_indptr,
                         const int32_t* d_indices, const float* d_data, int32_t k, int32_t solver, int32_t max_iter,
                         double tol, uint64_t seed, float* d_x_pca, float* d_components, double* h_var,
-                        double* h_var_ratio, double* h_mean, sb2_pca_info* info) {
-  SB2_CHECK_ARG(ctx && d_indptr && d_x_pca && d_components && h_var && h_var_ratio && h_mean, "null pointer");
+                        double* h_var_ratio, double* h_mean, sb2_pca_info* info, const double* pre_stats,
+                        const double* pre_gram, float* d_proj_out, float* d_shift_out, int32_t* l_out) {
+  const bool streamed = pre_stats != nullptr;
+  SB2_CHECK_ARG(ctx && (streamed || (d_indptr && d_x_pca)) && d_components && h_var && h_var_ratio && h_mean, "null pointer");
+  SB2_CHECK_ARG(!streamed || (pre_gram && d_proj_out && d_shift_out && l_out), "streamed PCA needs the Gram matrix and the projection outputs");
+  if (streamed) solver = 1;
   SB2_CHECK_ARG(n >= 0 && n_total >= n && n_total >= 2 && g >= 1, "shape");
   SB2_CHECK_ARG(k >= 1 && k < std::min<int64_t>(n_total, g), "n_components must be between 1 and min(n_samples, n_features)-1");
   SB2_CHECK_ARG(k <= 120, "n_components <= 120");
@@ -814,8 +822,12 @@ int32_t sb2_pca_csr_f32(sb2_ctx* ctx, int64_t n, int64_t n_total, int32_t g, con
   double *d_sum, *d_sumsq;
   SB2_TRY(scr.alloc(&d_sum, (size_t)2 * g));
   d_sumsq = d_sum + g;
-  SB2_TRY(sb2_csr_col_stats(ctx, n, g, d_indptr, d_indices, d_data, d_sum, d_sumsq));
-  SB2_TRY(sb2_comm_allreduce_f64(ctx, d_sum, 2 * (int64_t)g));
+  if (streamed) {
+    SB2_CUDA(cudaMemcpyAsync(d_sum, pre_stats, sizeof(double) * 2 * g, cudaMemcpyDeviceToDevice, st));
+  } else {
+    SB2_TRY(sb2_csr_col_stats(ctx, n, g, d_indptr, d_indices, d_data, d_sum, d_sumsq));
+    SB2_TRY(sb2_comm_allreduce_f64(ctx, d_sum, 2 * (int64_t)g));
+  }
   std::vector<double> hs(2 * (size_t)g);
   SB2_CUDA(cudaMemcpyAsync(hs.data(), d_sum, sizeof(double) * 2 * g, cudaMemcpyDeviceToHost, st));
   SB2_CUDA(cudaStreamSynchronize(st));
@@ -846,7 +858,11 @@ int32_t sb2_pca_csr_f32(sb2_ctx* ctx, int64_t n, int64_t n_total, int32_t g, con
   SB2_TRY(scr.alloc(&w.d_Bf, (size_t)gp * l));
   if (solver == 1) {
     SB2_TRY(scr.alloc(&w.d_C, (size_t)gp * gp));
-    if (gp == g) {
+    if (streamed) {
+      SB2_CUDA(cudaMemsetAsync(w.d_C, 0, sizeof(double) * (size_t)gp * gp, st));
+      SB2_CUDA(cudaMemcpy2DAsync(w.d_C, sizeof(double) * gp, pre_gram, sizeof(double) * g, sizeof(double) * g, g,
+                                 cudaMemcpyDeviceToDevice, st));
+    } else if (gp == g) {
       SB2_TRY(sb2_csr_gram(ctx, n, g, d_indptr, d_indices, d_data, w.d_C));
     } else {
       double* Gs;
@@ -856,7 +872,7 @@ int32_t sb2_pca_csr_f32(sb2_ctx* ctx, int64_t n, int64_t n_total, int32_t g, con
       SB2_CUDA(cudaMemcpy2DAsync(w.d_C, sizeof(double) * gp, Gs, sizeof(double) * g, sizeof(double) * g, g,
                                  cudaMemcpyDeviceToDevice, st));
     }
-    SB2_TRY(sb2_comm_allreduce_f64(ctx, w.d_C, (int64_t)gp * gp));
+    if (!streamed) SB2_TRY(sb2_comm_allreduce_f64(ctx, w.d_C, (int64_t)gp * gp));
     if (gp != g) {  // mu padded with zeros
       double* mup;
       SB2_TRY(scr.alloc(&mup, (size_t)gp));
@@ -1010,7 +1026,13 @@ int32_t sb2_pca_csr_f32(sb2_ctx* ctx, int64_t n, int64_t n_total, int32_t g, con
     SB2_TRY(scr.alloc(&d_shift, (size_t)l));
     mu_dot_kernel<<<l, 256, 0, st>>>(w.d_mu, d_V, g, l, d_shift);
     SB2_LAUNCH_CHECK(ctx);
-    SB2_TRY(launch_spmm(ctx, n, l, d_indptr, d_indices, d_data, w.d_Bf, d_shift, d_x_pca, k, k));
+    if (streamed) {
+      SB2_CUDA(cudaMemcpyAsync(d_proj_out, w.d_Bf, sizeof(float) * (size_t)g * l, cudaMemcpyDeviceToDevice, st));
+      SB2_CUDA(cudaMemcpyAsync(d_shift_out, d_shift, sizeof(float) * l, cudaMemcpyDeviceToDevice, st));
+      *l_out = l;
+    } else {
+      SB2_TRY(launch_spmm(ctx, n, l, d_indptr, d_indices, d_data, w.d_Bf, d_shift, d_x_pca, k, k));
+    }
   }
   for (int j = 0; j < k; ++j) {
     const double ev = std::max(theta[j], 0.0) / (nt - 1.0);  // explained_variance_ = S^2/(n-1) (_pca.py:760-779)
@@ -1025,6 +1047,59 @@ int32_t sb2_pca_csr_f32(sb2_ctx* ctx, int64_t n, int64_t n_total, int32_t g, con
     info->total_var = total_var;
   }
   return SB2_OK;
+}
+
+int32_t sb2_pca_csr_f32(sb2_ctx* ctx, int64_t n, int64_t n_total, int32_t g, const int64_t* d_indptr,
+                        const int32_t* d_indices, const float* d_data, int32_t k, int32_t solver, int32_t max_iter,
+                        double tol, uint64_t seed, float* d_x_pca, float* d_components, double* h_var,
+                        double* h_var_ratio, double* h_mean, sb2_pca_info* info) {
+  return pca_core(ctx, n, n_total, g, d_indptr, d_indices, d_data, k, solver, max_iter, tol, seed, d_x_pca, d_components, h_var,
+                  h_var_ratio, h_mean, info, nullptr, nullptr, nullptr, nullptr, nullptr);
+}
+
+// ---- out-of-core / chunked PCA (sc.pp.pca(chunked=True), src/scanpy/preprocessing/_pca/__init__.py:245-271) ----
+// The reference streams row chunks through sklearn's IncrementalPCA and its own test asks the result to equal the full PCA
+// (tests/test_pca.py:357-386, rtol 1e-6).  Here the row chunks stream through the EXACT Gram route instead: pass 1
+// accumulates column sums and X^T X chunk by chunk (this call), sb2_pca_stream_solve_f32 diagonalises the covariance,
+// pass 2 projects each chunk (sb2_pca_stream_project_f32).  Device memory: one chunk + 2 g^2 doubles, whatever n is.
+static __global__ void add_f64_kernel(int64_t n, const double* __restrict__ a, double* __restrict__ acc) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) acc[i] += a[i];
+}
+int32_t sb2_pca_stream_accumulate_f32(sb2_ctx* ctx, int64_t n_chunk, int32_t g, const int64_t* d_indptr,
+                                      const int32_t* d_indices, const float* d_data, double* d_stats, double* d_gram) {
+  SB2_CHECK_ARG(ctx && d_indptr && d_stats && d_gram && g >= 1 && n_chunk >= 0, "null pointer / shape");
+  SB2_CUDA(cudaSetDevice(ctx->device));
+  if (n_chunk == 0) return SB2_OK;
+  ScratchScope scr(ctx);
+  double *st2, *G;
+  SB2_TRY(scr.alloc(&st2, (size_t)2 * g));
+  SB2_TRY(scr.alloc(&G, (size_t)g * g));
+  SB2_TRY(sb2_csr_col_stats(ctx, n_chunk, g, d_indptr, d_indices, d_data, st2, st2 + g));
+  SB2_TRY(sb2_csr_gram(ctx, n_chunk, g, d_indptr, d_indices, d_data, G));
+  add_f64_kernel<<<(unsigned)ceil_div64(2 * (int64_t)g, 256), 256, 0, ctx->stream>>>(2 * (int64_t)g, st2, d_stats);
+  SB2_LAUNCH_CHECK(ctx);
+  add_f64_kernel<<<(unsigned)ceil_div64((int64_t)g * g, 256), 256, 0, ctx->stream>>>((int64_t)g * g, G, d_gram);
+  SB2_LAUNCH_CHECK(ctx);
+  return SB2_OK;
+}
+int32_t sb2_pca_stream_solve_f32(sb2_ctx* ctx, int64_t n_total, int32_t g, const double* d_stats, const double* d_gram,
+                                 int32_t k, int32_t max_iter, double tol, uint64_t seed, float* d_components, double* h_var,
+                                 double* h_var_ratio, double* h_mean, float* d_proj, float* d_shift, int32_t* h_l,
+                                 sb2_pca_info* info) {
+  SB2_CHECK_ARG(d_stats && d_gram && d_proj && d_shift && h_l, "null pointer");
+  SB2_CHECK_ARG(n_total >= 2 && g >= 1, "shape");
+  SB2_CHECK_ARG(k >= 1 && k < std::min<int64_t>(n_total, g), "n_components must be between 1 and min(n_samples, n_features)-1");
+  return pca_core(ctx, 0, n_total, g, nullptr, nullptr, nullptr, k, 1, max_iter, tol, seed, nullptr, d_components, h_var,
+                  h_var_ratio, h_mean, info, d_stats, d_gram, d_proj, d_shift, h_l);
+}
+int32_t sb2_pca_stream_project_f32(sb2_ctx* ctx, int64_t n_chunk, int32_t g, const int64_t* d_indptr,
+                                   const int32_t* d_indices, const float* d_data, int32_t k, int32_t l, const float* d_proj,
+                                   const float* d_shift, float* d_x_pca) {
+  SB2_CHECK_ARG(ctx && d_indptr && d_proj && d_shift && d_x_pca, "null pointer");
+  SB2_CHECK_ARG(k >= 1 && k <= l && (l == 32 || l == 64 || l == 128), "k / l");
+  SB2_CUDA(cudaSetDevice(ctx->device));
+  return launch_spmm(ctx, n_chunk, l, d_indptr, d_indices, d_data, d_proj, d_shift, d_x_pca, k, k);
 }
 
 }  // extern "C"

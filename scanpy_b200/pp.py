@@ -70,8 +70,6 @@ def pca(data, n_comps: int | None = None, *, layer: str | None = None, obsm: str
     start = log_start("computing PCA")
     if (layer is not None or obsm is not None) and chunked:
         raise NotImplementedError("Cannot use `layer`/`obsm` and `chunked` at the same time.")
-    if chunked:
-        raise NotImplementedError("`chunked=True` (IncrementalPCA) is not implemented in scanpy_b200.")
     if not zero_center:
         raise NotImplementedError("`zero_center=False` (TruncatedSVD) is not implemented in scanpy_b200.")
     return_anndata = is_anndata_like(data)
@@ -106,7 +104,13 @@ def pca(data, n_comps: int | None = None, *, layer: str | None = None, obsm: str
                          f"{min(n_obs, n_vars)!r} with svd_solver='arpack'")
     xc = as_csr_f32(x)
     solver = _solver_code(svd_solver, n_vars=n_vars)
-    out = _ops.pca_csr(xc, n_comps, solver=solver, seed=seed_from_rng(rng))
+    if chunked:
+        # the reference feeds row chunks to IncrementalPCA and expects the full PCA's result (tests/test_pca.py:357-386);
+        # here the chunks stream through the exact Gram route (out-of-core: one chunk on the device at a time)
+        out = _ops.pca_csr_chunked(xc, n_comps, chunk_size=settings.chunk_size if chunk_size is None else chunk_size,
+                                   seed=seed_from_rng(rng))
+    else:
+        out = _ops.pca_csr(xc, n_comps, solver=solver, seed=seed_from_rng(rng))
     if not out["converged"]:
         # the block iteration stopped on stagnation / its iteration cap before the residual test was met (the SpMM-driven
         # solver works in float32 passes and can sit on its rounding floor): never silently different

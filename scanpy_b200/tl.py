@@ -177,3 +177,6 @@ def _natkey(s: str):
     import re
 
     return [int(t) if t.isdigit() else t for t in re.split(r"(\d+)", s)]
+
+
+from ._graph_tools import diffmap, paga, umap  # noqa: E402,F401  

@@ -107,6 +107,7 @@ def test_louvain_vs_networkx_and_planted(graph_small):
     import networkx as nx
 
     ad, lab = graph_small
+    ad = ad.copy()
     sb.tl.louvain(ad, use_weights=True)
     got = ad.obs["louvain"].to_numpy().astype(int)
     assert ad.uns["louvain"]["params"] == dict(resolution=None, random_state=0)
@@ -174,3 +175,175 @@ def test_metrics_modularity_api(graph_small):
         sb.metrics.modularity(conn, labels)
     with pytest.raises(ValueError, match="undirected"):
         sb.metrics.modularity(ad, is_directed=True)
+
+
+# ------------------------------------------------------------------------------------------ tl.umap
+@pytest.fixture(scope="module")
+def overlap_graph():
+    """Six overlapping Gaussian clusters in 10-D (connected kNN graph), UMAP connectivities from the device."""
+    rng = np.random.default_rng(0)
+    cent = rng.normal(size=(6, 10)) * 2.0
+    x = np.concatenate([rng.normal(size=(400, 10)) + cent[c] for c in range(6)]).astype(np.float32)
+    lab = np.repeat(np.arange(6), 400)
+    ad = sb.MiniAnnData(x)
+    sb.pp.neighbors(ad, n_neighbors=15, use_rep="X")
+    return ad, x, lab
+
+
+def test_umap_quality_matches_sequential_oracle(overlap_graph):
+    from sklearn.manifold import trustworthiness
+    from sklearn.metrics import silhouette_score
+
+    from oracle import graph_tools as og
+
+    ad, x, lab = overlap_graph
+    ad = ad.copy()
+    conn_before = ad.obsp["connectivities"].copy()
+    sb.tl.umap(ad)
+    emb = ad.obsm["X_umap"]
+    assert emb.shape == (len(x), 2) and emb.dtype == np.float32 and np.isfinite(emb).all()
+    # parameters recorded like the reference (a, b of find_ab_params(1.0, 0.5); random_state 0)
+    p = ad.uns["umap"]["params"]
+    assert p["a"] == pytest.approx(0.5830300, rel=1e-5) and p["b"] == pytest.approx(1.3341669, rel=1e-5)
+    assert p["random_state"] == 0
+    # tests/test_embedding.py:83-96: the graph is not touched, no explicit zeros
+    conn = ad.obsp["connectivities"]
+    assert (conn.data == conn_before.data).all() and conn.nnz == conn_before.nnz and (conn.data == 0).sum() == 0
+    ref = og.simplicial_set_embedding(conn_before, a=p["a"], b=p["b"])
+    t_got, t_ref = trustworthiness(x, emb, n_neighbors=15), trustworthiness(x, ref, n_neighbors=15)
+    s_got, s_ref = silhouette_score(emb, lab), silhouette_score(ref, lab)
+    assert t_got > t_ref - 0.02, (t_got, t_ref)
+    assert s_got > s_ref - 0.1, (s_got, s_ref)
+    # layout scale comparable with the sequential optimiser's (same forces, same schedule)
+    assert 0.3 < emb.std() / ref.std() < 3.0
+
+
+def test_umap_init_dtype_keys_and_seeds(overlap_graph):
+    ad, x, _ = overlap_graph
+    # tests/test_embedding.py:48-66: float32 / float64 initial positions give the same embedding; params recorded per key
+    a1, a2 = ad.copy(), ad.copy()
+    init = x[:, :2]
+    sb.tl.umap(a1, init_pos=init.astype(np.float32), maxiter=100)
+    sb.tl.umap(a2, init_pos=init.astype(np.float64), maxiter=100, key_added="custom_key")
+    np.testing.assert_array_almost_equal(a1.obsm["X_umap"], a2.obsm["custom_key"])
+    assert a1.uns["umap"]["params"]["a"] == a2.uns["custom_key"]["params"]["a"]
+    assert a1.uns["umap"]["params"]["b"] == a2.uns["custom_key"]["params"]["b"]
+    # an .obsm key as init_pos, 3 components, random init; same seed -> same layout, other seed -> another
+    a1.obsm["my_init"] = np.ascontiguousarray(x[:, :3])
+    sb.tl.umap(a1, init_pos="my_init", n_components=3, maxiter=50, key_added="u3")
+    assert a1.obsm["u3"].shape == (len(x), 3)
+    b1, b2, b3 = ad.copy(), ad.copy(), ad.copy()
+    sb.tl.umap(b1, init_pos="random", maxiter=50, random_state=3)
+    sb.tl.umap(b2, init_pos="random", maxiter=50, random_state=3)
+    sb.tl.umap(b3, init_pos="random", maxiter=50, random_state=4)
+    assert (b1.obsm["X_umap"] == b2.obsm["X_umap"]).all()
+    assert not (b1.obsm["X_umap"] == b3.obsm["X_umap"]).all()
+    with pytest.raises(ValueError, match="Run `sc.pp.neighbors` first"):
+        sb.tl.umap(sb.MiniAnnData(x))
+    with pytest.raises(ValueError, match="Unknown method"):
+        sb.tl.umap(ad.copy(), method="nope")
+
+
+# ------------------------------------------------------------------------------------------ tl.diffmap
+def test_diffmap_matches_reference_eigsh(overlap_graph):
+    from oracle import graph_tools as og
+
+    ad, _, _ = overlap_graph
+    ad = ad.copy()
+    sb.tl.diffmap(ad, n_comps=15)
+    evals = ad.uns["diffmap_evals"]
+    basis = ad.obsm["X_diffmap"]
+    ref_evals, ref_basis = og.diffmap_eigen(ad.obsp["connectivities"], 15, seed=0)
+    assert evals.dtype == np.float32 and basis.dtype == np.float32 and basis.shape == (ad.n_obs, 15)
+    assert (np.diff(evals) <= 1e-7).all()  # sort='decrease'
+    np.testing.assert_allclose(evals, ref_evals, atol=2e-6)
+    # eigenvectors up to sign where the eigenvalue is isolated; the spanned subspace everywhere
+    gaps = np.minimum(np.abs(np.diff(ref_evals, prepend=np.inf)), np.abs(np.diff(ref_evals, append=-np.inf)))
+    for c in np.flatnonzero(gaps > 1e-3):
+        dot = abs(float(basis[:, c].astype(np.float64) @ ref_basis[:, c].astype(np.float64)))
+        assert dot > 1 - 1e-4, (c, dot, gaps[c])
+    q, _ = np.linalg.qr(ref_basis.astype(np.float64))
+    resid = basis.astype(np.float64) - q @ (q.T @ basis.astype(np.float64))
+    assert np.abs(resid).max() < 1e-3
+    np.testing.assert_allclose(np.linalg.norm(basis.astype(np.float64), axis=0), 1.0, atol=1e-5)
+
+
+def test_diffmap_seeds_and_keys(overlap_graph):
+    # tests/test_embedding.py:99-139: same seed reproducible, other seed differs (bitwise), key_added layouts
+    ad, _, _ = overlap_graph
+    d1, d2, d3 = (sb.tl.diffmap(ad, copy=True, random_state=s).obsm["X_diffmap"].copy() for s in (0, 0, 1234))
+    np.testing.assert_array_equal(d1, d2)
+    assert not np.array_equal(d1, d3)
+    a = sb.tl.diffmap(ad, key_added="custom_key", copy=True, n_comps=5)
+    assert "custom_key" in a.obsm and isinstance(a.uns["custom_key"], dict) and len(a.uns["custom_key"]["evals"]) == 5
+    with pytest.raises(ValueError, match="greater than 2"):
+        sb.tl.diffmap(ad.copy(), n_comps=2)
+    with pytest.raises(ValueError, match="pp.neighbors"):
+        sb.tl.diffmap(sb.MiniAnnData(np.zeros((5, 3), np.float32)))
+
+
+def test_eigsh_ends_of_the_spectrum(overlap_graph):
+    """sb2_eigsh_csr_scaled against scipy's eigsh on the same operator: largest / smallest algebraic, unscaled."""
+    from scipy.sparse.linalg import eigsh
+
+    from scanpy_b200 import _abi, _ops
+
+    ad, _, _ = overlap_graph
+    conn = ad.obsp["connectivities"].tocsr().astype(np.float32)
+    ctx = _abi.default_context()
+    dp, di, dw = _ops.csr_to_device(conn)
+    for which in ("LA", "SA"):
+        ev, vecs, info = _ops.eigsh_scaled_device(ctx, dp, di, dw, conn.shape[0], 4, which=which)
+        ref = eigsh(conn.astype(np.float64), k=4, which=which)[0]
+        np.testing.assert_allclose(ev, np.sort(ref), rtol=1e-8, atol=1e-8)
+        v = _ops._to_host(vecs)
+        # residual |A v - lambda v| of every returned pair
+        r = conn.astype(np.float64) @ v.T - v.T * ev
+        assert np.abs(r).max() < 1e-6 and info["n_converged"] == 4
+
+
+# ------------------------------------------------------------------------------------------ tl.paga
+def test_paga_matches_oracle(graph_small):
+    from oracle import graph_tools as og
+
+    ad, _ = graph_small
+    ad = ad.copy()
+    sb.tl.leiden(ad, flavor="igraph")
+    sb.tl.paga(ad)
+    assert ad.uns["paga"]["groups"] == "leiden"
+    codes = ad.obs["leiden"].cat.codes.to_numpy()
+    conn, tree, ns = og.paga_v1_2(ad.obsp["distances"], codes)
+    np.testing.assert_array_equal(ad.uns["leiden_sizes"], ns)
+    np.testing.assert_allclose(ad.uns["paga"]["connectivities"].toarray(), conn.toarray(), rtol=1e-12)
+    np.testing.assert_allclose(ad.uns["paga"]["connectivities_tree"].toarray(), tree.toarray(), rtol=1e-12)
+    c = ad.uns["paga"]["connectivities"]
+    assert abs(c - c.T).max() < 1e-12 and c.max() <= 1.0
+    with pytest.raises(KeyError, match="not found"):
+        sb.tl.paga(ad, groups="nope")
+    with pytest.raises(ValueError, match="tl.leiden"):
+        sb.tl.paga(graph_small[0].copy())
+
+
+# ------------------------------------------------------------------------------------------ chunked / out-of-core PCA
+def test_pca_chunked_equals_full():
+    """tests/test_pca.py:357-386: chunked PCA == default PCA (rtol 1e-6 there on |X_pca|, |PCs|, variance, variance_ratio);
+    plus the fp64 truth bar of the hot path (1e-4 relative per component)."""
+    from oracle import pca as opca
+
+    x, _ = synth_scipy(7000, 700, n_clusters=8, r=40)
+    full, chunked = sb.MiniAnnData(x), sb.MiniAnnData(x)
+    sb.pp.pca(full, n_comps=30, svd_solver="covariance_eigh")
+    sb.pp.pca(chunked, n_comps=30, chunked=True, chunk_size=1111)  # 7 ragged chunks
+    a, b = np.abs(full.obsm["X_pca"]), np.abs(chunked.obsm["X_pca"])
+    scale = np.abs(full.obsm["X_pca"]).max(axis=0)
+    assert (np.abs(a - b) / scale).max() < 2e-6
+    np.testing.assert_allclose(np.abs(chunked.varm["PCs"]), np.abs(full.varm["PCs"]), atol=2e-6)
+    np.testing.assert_allclose(chunked.uns["pca"]["variance"], full.uns["pca"]["variance"], rtol=1e-6)
+    np.testing.assert_allclose(chunked.uns["pca"]["variance_ratio"], full.uns["pca"]["variance_ratio"], rtol=1e-6)
+    ref = opca.pca_arpack(x.astype(np.float64), 30, dtype="float64")
+    xp = opca.align_signs(chunked.obsm["X_pca"].astype(np.float64), ref["X_pca"])
+    rel = np.linalg.norm(xp - ref["X_pca"], axis=0) / np.linalg.norm(ref["X_pca"], axis=0)
+    assert rel.max() < 1e-4
+    # one chunk larger than the matrix, and the plain-array entry point
+    xp1 = sb.pp.pca(x, n_comps=10, chunked=True, chunk_size=10**6)
+    np.testing.assert_allclose(np.abs(xp1), np.abs(full.obsm["X_pca"][:, :10]), atol=5e-5 * scale[:10].max())

@@ -180,7 +180,7 @@ def test_struct_layouts_match_the_header(tmp_path):
         pytest.skip("gcc not available")
     root = Path(__file__).resolve().parents[1]
     structs = {"sb2_device_info": _abi.DeviceInfo, "sb2_pca_info": _abi.PcaInfo, "sb2_knn_info": _abi.KnnInfo,
-               "sb2_leiden_info": _abi.LeidenInfo}
+               "sb2_leiden_info": _abi.LeidenInfo, "sb2_eigs_info": _abi.EigsInfo}
     lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "scanpy_b200.h"', "int main(void) {"]
     for cname, cls in structs.items():
         lines.append(f'  printf("{cname} %zu", sizeof({cname}));')

@@ -185,3 +185,33 @@ def test_scale_oracle_reproduces_reference_goldens(sp, zero_center, masked):
     assert np.allclose(std, [1, 1, 2, 1])  # "gene std 1,0,2,0" with the zeros replaced by 1
     clipped, _, _ = opre.scale(x0, zero_center=False, max_value=1, mask_obs=mask)
     assert np.allclose(clipped, L["X_scaled_for_mask_clipped"] if masked else L["X_scaled_original_clipped"])
+
+
+# ------------------------------------------------------------------------------------------ graph-tool oracles
+def test_graph_tool_oracles_on_the_reference_fixture(pbmc68k_graph):
+    """oracle.graph_tools on the reference's in-tree pbmc68k_reduced graph: the diffusion-map spectrum is a transition
+    matrix's (top eigenvalue 1, all within [-1, 1]), PAGA v1.2 on the stored louvain labels is symmetric in [0, 1] with a
+    spanning tree of G-1 edges per connected component, and the sequential UMAP restatement separates the clusters."""
+    from scipy import sparse
+    from scipy.sparse.csgraph import connected_components
+    from sklearn.metrics import silhouette_score
+
+    from oracle import graph_tools as og
+
+    f = pbmc68k_graph
+    n = len(f["conn_indptr"]) - 1
+    conn = sparse.csr_matrix((f["conn_data"], f["conn_indices"], f["conn_indptr"]), shape=(n, n))
+    dist = sparse.csr_matrix((f["dist_data"], f["dist_indices"], f["dist_indptr"]), shape=(n, n))
+    evals, evecs = og.diffmap_eigen(conn, 10)
+    assert evals[0] == pytest.approx(1.0, abs=1e-6) and (np.abs(evals) <= 1 + 1e-6).all() and (np.diff(evals) <= 0).all()
+    t = og.transitions_sym(conn).astype(np.float64)
+    assert abs(t - t.T).max() < 1e-7
+    np.testing.assert_allclose(t @ evecs[:, 1].astype(np.float64), evals[1] * evecs[:, 1].astype(np.float64), atol=1e-5)
+    codes = f["louvain_codes"].astype(int)
+    c, tree, ns = og.paga_v1_2(dist, codes)
+    G = codes.max() + 1
+    assert ns.sum() == n and c.shape == (G, G) and abs(c - c.T).max() < 1e-12 and 0 < c.max() <= 1
+    ncomp = connected_components(c)[0]
+    assert tree.nnz == G - ncomp
+    emb = og.simplicial_set_embedding(conn.astype(np.float32), n_epochs=200)
+    assert np.isfinite(emb).all() and silhouette_score(emb, codes) > 0.1
