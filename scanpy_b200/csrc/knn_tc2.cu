@@ -261,8 +261,12 @@ __device__ __forceinline__ void est_chunk(float (&est)[LEN], const uint32_t (&v)
 // Sweep front: CTAs walk the candidate tiles cyclically, each starting where the CTAs already running currently are
 // (the order of the candidates is irrelevant to the result).  All resident CTAs then stream the same few tiles at the
 // same time and the candidate images (166 MB at 1.3M x 50, more than the L2) are read from HBM about once per wave of
-// CTAs instead of once per CTA.
-__device__ int32_t g_knn2_front;
+// CTAs instead of once per CTA.  "Where the running CTAs are" is the MEAN position of the pack, (sweep visits so far) /
+// (resident CTAs): the first version started a new CTA at the position last published by ANY running CTA, so the
+// spread of the pack was inherited and widened from wave to wave (a random walk over 68 waves: ncu showed 114 GB of
+// DRAM reads per launch, L2 hit rate 77 %, profiles/r2_ncu_metrics_knn_sweep2.txt); re-centring every new CTA on the
+// mean bounds the spread by the drift of a single lap.
+__device__ unsigned long long g_knn2_front;   // sweep-proper visits of all CTAs of this launch, in units of 16 tiles
 __device__ unsigned long long g_knn2_stamp[4];
 __device__ unsigned long long g_knn2_phase[2][8];
 __device__ __forceinline__ unsigned long long gtimer_ns() {
@@ -300,8 +304,12 @@ knn_sweep2_kernel(const __half* __restrict__ Aimg, const __half* __restrict__ Bi
     mbar_init(afull, 1);
     for (int b = 0; b < 2; ++b) { mbar_init(&tfull[b], 1); mbar_init(&tempty[b], NEPI); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    const int32_t f = *reinterpret_cast<volatile int32_t*>(&g_knn2_front);
-    *start_tile = (f >= 0 && (int64_t)f < n_btiles) ? f : 0;
+    const unsigned long long f = *reinterpret_cast<volatile unsigned long long*>(&g_knn2_front);
+    unsigned int nsm;
+    asm volatile("mov.u32 %0, %%nsmid;" : "=r"(nsm));
+    const unsigned long long resident = min((unsigned long long)gridDim.x, (unsigned long long)max(nsm, 1u));
+    // mean tile of the pack now, plus the n_est visits this CTA spends on its threshold estimate before it joins
+    *start_tile = (int32_t)((f * 16ull / resident + (unsigned long long)n_est) % (unsigned long long)n_btiles);
   }
   if (warp == W_MMA) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u) : "memory");
@@ -472,7 +480,7 @@ knn_sweep2_kernel(const __half* __restrict__ Aimg, const __half* __restrict__ Bi
       if (!NOSCAN) { if (estimating) est_chunk(L.ls, v); else scan_chunk(L, id, v, cbase + 32, n_points); }
       SB2_PH(5)
       if (!estimating) {
-        if ((c & 15) == 0 && warp == 0 && lane == 0) *reinterpret_cast<volatile int32_t*>(&g_knn2_front) = ctile;   // publish the front
+        if ((c & 15) == 0 && warp == 0 && lane == 0) atomicAdd(&g_knn2_front, 1ull);   // 16 more visits of the pack
         cbase += CN;
         if (++ctile == n_bt) { ctile = 0; cbase = cq * 64; }
       }
@@ -580,7 +588,7 @@ int32_t knn_tc2_sweep(sb2_ctx* ctx, const KnnTc2Shape& sh, const __half* Aimg, i
   {
     void* fp = nullptr;
     SB2_CUDA(cudaGetSymbolAddress(&fp, g_knn2_front));
-    SB2_CUDA(cudaMemsetAsync(fp, 0, sizeof(int32_t), st));
+    SB2_CUDA(cudaMemsetAsync(fp, 0, sizeof(unsigned long long), st));
   }
   cudaError_t le;
 #define SB2_L2(NGV, MODEV) launch2<NGV, MODEV>(grid, sh, st, Aimg, Bimg, n_tiles, n_est, est_stride, a_tile0, n_query, np, cand_score, cand_idx)
