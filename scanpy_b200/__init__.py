@@ -9,6 +9,7 @@ in hand-written CUDA behind the C ABI in include/scanpy_b200.h; there is no CPU 
 """
 from . import metrics, pp, tl  # noqa: F401
 from ._compat import MiniAnnData, settings  # noqa: F401
+from ._io import ZarrCSR, read_zarr_backed  # noqa: F401
 from .transformer import B200KNNTransformer, B200PCA  # noqa: F401
 
 __version__ = "0.1.0"

@@ -153,6 +153,10 @@ def pca_csr_chunked(x, n_comps: int, *, chunk_size: int, seed: int = 0, ctx=None
     gram = torch.zeros((g, g), dtype=torch.float64, device="cuda")
 
     def chunks():
+        if hasattr(x, "row_chunks"):   # on-disk matrix (scanpy_b200._io.ZarrCSR): only the chunk is ever in host memory
+            for r0, r1, indptr, indices, data in x.row_chunks(chunk_size):
+                yield r0, r1, _to_device(indptr), _to_device(indices), _to_device(data)
+            return
         for r0 in range(0, n, chunk_size):
             r1 = min(n, r0 + chunk_size)
             lo, hi = int(x.indptr[r0]), int(x.indptr[r1])

@@ -163,8 +163,8 @@ csr_gram_kernel(int64_t n, const int64_t* __restrict__ indptr, const int32_t* __
   }
 }
 
-// ---- Gram matrix, second generation: column-blocked tiles accumulated in shared memory -----------------------------------
-// The first-generation kernel above issues one global fp64 RED per product (6.5e9 at 1.3M x 2000, ~170 G RED/s = 38 ms).
+// ---- Gram matrix, tiled variant (opt-in, SB2_GRAM_TILED=1; measured slower than the kernel above, see sb2_csr_gram) ----------
+// The kernel above issues one global fp64 RED per product (6.5e9 at 1.3M x 2000, ~195 G RED/s = 33 ms).
 // Here the g columns are cut into NB blocks of GT_W; a CTA owns one tile pair (bi <= bj) of G for a contiguous range of
 // rows and keeps that GT_W x GT_W fp64 tile in shared memory (128 KB): for every row, the entries falling into blocks bi
 // and bj (contiguous, rows are column-sorted; their positions come from a per-row block-offset table built once) are
@@ -875,8 +875,12 @@ int32_t sb2_csr_gram(sb2_ctx* ctx, int64_t n, int32_t g, const int64_t* d_indptr
   SB2_CUDA(cudaMemsetAsync(d_gram, 0, sizeof(double) * (size_t)g * g, ctx->stream));
   bool done = false;
   const int NB = (int)ceil_div64(g, GT_W);
-  static const bool force_v1 = getenv("SB2_GRAM_V1") != nullptr;
-  if (n >= 2048 && g >= 64 && NB <= 63 && !force_v1) {
+  // MEASURED AND NOT ADOPTED (B200, scripts/r2_gram.py, profiles/README.md): at 1.3M x 2000 the tiled kernel takes 95.5 ms
+  // against 33.4 ms for the one-RED-per-product kernel (100k rows: 7.3 vs 2.7 ms), same result to 6e-14.  Shared-memory
+  // fp64 atomicAdd is a CAS loop (ATOMS.CAST.SPIN.64) behind a chain of dependent global loads (block offsets ->
+  // indices/data) with 16 warps per SM to hide it, while the L2 retires ~195 G fp64 REDs/s.  Kept opt-in (SB2_GRAM_TILED=1).
+  static const bool use_tiled = getenv("SB2_GRAM_TILED") != nullptr;
+  if (n >= 2048 && g >= 64 && NB <= 63 && use_tiled) {
     // tiled kernel: needs column-sorted rows (checked while the block-offset table is built)
     ScratchScope scr(ctx);
     uint16_t* boff;

@@ -92,7 +92,12 @@ def pca(data, n_comps: int | None = None, *, layer: str | None = None, obsm: str
         x = adata.X
     if type(x).__module__.startswith("dask"):
         raise NotImplementedError("dask arrays are not supported by scanpy_b200.pp.pca")
+    backed = hasattr(x, "row_chunks")  # on-disk CSR (scanpy_b200._io.ZarrCSR)
+    if backed and not chunked:
+        raise NotImplementedError("an on-disk matrix can only be processed with `chunked=True` in scanpy_b200.pp.pca")
     if mask_var is not None:
+        if backed:
+            raise NotImplementedError("`mask_var` on an on-disk matrix is not implemented in scanpy_b200.pp.pca")
         x = x[:, mask_var]
     n_obs, n_vars = x.shape
     if n_comps is None:
@@ -102,7 +107,7 @@ def pca(data, n_comps: int | None = None, *, layer: str | None = None, obsm: str
         # sklearn's message for svd_solver='arpack' (pinned by tests/test_pca.py:292-296)
         raise ValueError(f"n_components={n_comps!r} must be between 1 and min(n_samples, n_features)="
                          f"{min(n_obs, n_vars)!r} with svd_solver='arpack'")
-    xc = as_csr_f32(x)
+    xc = x if backed else as_csr_f32(x)
     solver = _solver_code(svd_solver, n_vars=n_vars)
     if chunked:
         # the reference feeds row chunks to IncrementalPCA and expects the full PCA's result (tests/test_pca.py:357-386);

@@ -1,4 +1,4 @@
-"""sb2_csr_gram at the bench workload: tiled kernel (default) vs first generation (SB2_GRAM_V1=1 in a second process), result
+"""sb2_csr_gram at the bench workload: one-RED-per-product kernel (default) vs the tiled shared-memory variant (SB2_GRAM_TILED=1 in a second process), result
 equality and CUDA-event timings.  usage: python scripts/r2_gram.py [n]"""
 import os, sys
 sys.path.insert(0, ".")
@@ -20,7 +20,7 @@ ts = []
 for _ in range(5):
     e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
     e0.record(); run(); e1.record(); torch.cuda.synchronize(); ts.append(e0.elapsed_time(e1))
-tag = "v1" if os.environ.get("SB2_GRAM_V1") else "tiled"
+tag = "tiled" if os.environ.get("SB2_GRAM_TILED") else "v1"
 print(f"gram {tag}: n={n} min {min(ts):.2f} ms median {sorted(ts)[2]:.2f} ms; checksum {float(G.sum()):.10e} trace {float(G.diagonal().sum()):.10e}")
 if n <= 200_000:
     ref = (X.astype(np.float64).T @ X.astype(np.float64)).toarray()

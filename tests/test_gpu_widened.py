@@ -347,3 +347,21 @@ def test_pca_chunked_equals_full():
     # one chunk larger than the matrix, and the plain-array entry point
     xp1 = sb.pp.pca(x, n_comps=10, chunked=True, chunk_size=10**6)
     np.testing.assert_allclose(np.abs(xp1), np.abs(full.obsm["X_pca"][:, :10]), atol=5e-5 * scale[:10].max())
+
+
+def test_pca_chunked_from_an_on_disk_zarr_store(tmp_path):
+    """f4: rows stream from a zarr-v3 CSR store (sharded + zstd, as anndata writes it) through the device; X never exists in
+    host memory as a whole on the product side.  Result == the in-core PCA of the same matrix."""
+    import zarr_writer
+
+    x, _ = synth_scipy(5000, 600, n_clusters=6, r=40)
+    zarr_writer.write_csr_store(tmp_path / "x.zarr", x, mode="sharded", chunk=65536, inner=8192)
+    backed = sb.read_zarr_backed(tmp_path / "x.zarr")
+    sb.pp.pca(backed, n_comps=20, chunked=True, chunk_size=777)
+    full = sb.MiniAnnData(x)
+    sb.pp.pca(full, n_comps=20, svd_solver="covariance_eigh")
+    scale = np.abs(full.obsm["X_pca"]).max(axis=0)
+    assert (np.abs(np.abs(backed.obsm["X_pca"]) - np.abs(full.obsm["X_pca"])) / scale).max() < 2e-6
+    np.testing.assert_allclose(backed.uns["pca"]["variance"], full.uns["pca"]["variance"], rtol=1e-6)
+    with pytest.raises(NotImplementedError, match="chunked=True"):
+        sb.pp.pca(sb.read_zarr_backed(tmp_path / "x.zarr"), n_comps=5)
