@@ -385,10 +385,10 @@ def run_b200(a, rank, world, local_rank):
     if ki["pass1_tensor"]:
         # DRAM bytes per launch of the dominant kernel from the committed ncu capture of this exact workload
         # (profiles/r1_ncu_metrics_knn_tiered.txt: dram__bytes_read 12.388 GB + dram__bytes_write 0.780 GB)
-        traffic = 13.168e9 if (world == 1 and a.n_cells == 1_300_000 and a.n_pcs == 50 and a.k == 15) else None
+        traffic = 11.973e9 if (world == 1 and a.n_cells == 1_300_000 and a.n_pcs == 50 and a.k == 15) else None
         roofline = dict(bound="tensor", kernel="knn_pass1_tc_kernel", achieved=ach, peak=peak_tensor, unit="TFLOP/s",
                         frac=ach / peak_tensor, traffic=traffic,
-                        traffic_source=("profiles/r1_ncu_metrics_knn_tiered.txt (ncu --set full, main launch; algorithmic operand bytes: "
+                        traffic_source=("profiles/r2_ncu_metrics_knn_sweep2_meanfront.txt (ncu --set full of knn_sweep2_kernel, main launch, dram read + write; algorithmic operand bytes: "
                                         "0.33 GB of fp16 images)" if traffic else None),
                         peak_source=("MEASURED_PEAKS.json bf16_tflops_sustained (kernel timed inside a long step)" if peaks else "fallback 1.4 PFLOP/s sustained"),
                         launch_ms=ki["pass1_ms"], algorithmic_flops_per_launch=ki["pass1_flops"],
