@@ -136,7 +136,10 @@ def _pca_csr_overlapped(ctx, x, n_comps: int, seed: int, n_chunks: int = 8):
     """Gram-route PCA of a HOST scipy CSR with the upload hidden behind the first pass over the data: the CSR arrays go up
     in `n_chunks` row ranges on a side stream, and as each range lands the compute stream adds its column statistics and
     Gram matrix (sb2_pca_stream_accumulate_f32 - the out-of-core entry point, pointed at the resident arrays).  The
-    projection then runs over the whole resident matrix.  Same arithmetic as solver 1 up to the fp64 summation order."""
+    projection then runs over the whole resident matrix.  Same arithmetic as solver 1 up to the fp64 summation order.
+    OPT-IN (SB2_PCA_OVERLAP=1): measured on B200 at 1.3M x 2000 from page-locked arrays, pca() takes 78 ms of wall time
+    this way against 62 ms of device work, but the bench's e2e did not improve (0.489 s vs 0.471 s without it, within
+    box-to-box noise) - the 21 ms upload is already a small part of the step - so the plain upload stays the default."""
     torch = _torch()
     n, g = x.shape
     nnz = int(x.nnz)
@@ -218,7 +221,7 @@ def pca_csr(x, n_comps: int, *, solver: int = 0, max_iter: int = 0, tol: float =
     n, g = x.shape
     min_nnz = int(os.environ.get("SB2_PCA_OVERLAP_MIN_NNZ", OVERLAP_MIN_NNZ))
     if (solver == 1 and max_iter == 0 and tol == 0.0 and x.nnz >= min_nnz and getattr(ctx, "n_ranks", 1) == 1
-            and g >= 64 and os.environ.get("SB2_PCA_OVERLAP", "1") != "0"):
+            and g >= 64 and os.environ.get("SB2_PCA_OVERLAP", "0") == "1"):
         out = _pca_csr_overlapped(ctx, x, n_comps, seed)
         d_x_pca = out["X_pca"]
         out["X_pca"], out["components"] = _to_host(out["X_pca"], out["components"])

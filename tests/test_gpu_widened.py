@@ -378,7 +378,7 @@ def test_pca_overlapped_upload_equals_plain_upload(monkeypatch):
     x[3000:3400] = 0
     x = x.tocsr().astype(np.float32)
     x.eliminate_zeros()
-    monkeypatch.setenv("SB2_PCA_OVERLAP", "0")
+    monkeypatch.delenv("SB2_PCA_OVERLAP", raising=False)
     plain = _ops.pca_csr(x, 25, solver=1)
     monkeypatch.setenv("SB2_PCA_OVERLAP", "1")
     monkeypatch.setenv("SB2_PCA_OVERLAP_MIN_NNZ", "1")
