@@ -129,6 +129,13 @@ int32_t sb2_spmm_csr_t(sb2_ctx* ctx, int64_t n, int32_t g, int32_t l, const int6
 int32_t sb2_csr_gram(sb2_ctx* ctx, int64_t n, int32_t g, const int64_t* d_indptr, const int32_t* d_indices,
                      const float* d_data, double* d_gram);
 
+/* sc.pp.pca(zero_center=False): replaces sklearn.decomposition.TruncatedSVD (src/scanpy/preprocessing/_pca/__init__.py:309-336).
+ * Top-k singular triplets of X itself: d_x_pca = X V (= U Sigma), d_components = V^T with svd_flip(u_based_decision=False)
+ * signs, h_var = np.var(X V, axis=0) (ddof 0), h_var_ratio = h_var / sum of per-gene variances (ddof 0). */
+int32_t sb2_tsvd_csr_f32(sb2_ctx* ctx, int64_t n, int32_t g, const int64_t* d_indptr, const int32_t* d_indices,
+                         const float* d_data, int32_t k, int32_t solver, int32_t max_iter, double tol, uint64_t seed,
+                         float* d_x_pca, float* d_components, double* h_var, double* h_var_ratio, sb2_pca_info* info);
+
 /* ---- out-of-core / chunked PCA: sc.pp.pca(chunked=True) (src/scanpy/preprocessing/_pca/__init__.py:245-271) ----
  * The reference streams row chunks through sklearn.decomposition.IncrementalPCA and asserts the result equals the full PCA
  * (tests/test_pca.py:357-386).  Here the chunks stream through the exact Gram route: device memory = one chunk + 2 g^2

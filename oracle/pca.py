@@ -101,3 +101,14 @@ def pca_gram_f64(x, n_comps: int, *, rows=None):
     s = np.sqrt(np.maximum(w_all, 0.0))
     gaps = (s[:-1] - s[1:]) / s[:-1]
     return dict(X_pca=x_pca, components=vt, variance=w, variance_ratio=w / total_var, mean=mu, gaps=gaps)
+
+
+def truncated_svd_arpack(x, n_comps: int, dtype="float64"):
+    """The reference's `zero_center=False` call (src/scanpy/preprocessing/_pca/__init__.py:331-336) with the exact solver:
+    sklearn TruncatedSVD(algorithm='arpack') -> dict(X_pca, components, variance, variance_ratio, singular_values)."""
+    from sklearn.decomposition import TruncatedSVD
+
+    t = TruncatedSVD(n_components=n_comps, algorithm="arpack", random_state=0)
+    xp = t.fit_transform(x.astype(dtype))
+    return dict(X_pca=xp, components=t.components_, variance=t.explained_variance_, variance_ratio=t.explained_variance_ratio_,
+                singular_values=t.singular_values_)

@@ -67,6 +67,8 @@ SIGNATURES = {
     "sb2_pca_csr_f32": (c_int32, [c_void_p, c_int64, c_int64, c_int32, c_void_p, c_void_p, c_void_p, c_int32,
                                   c_int32, c_int32, c_double, c_uint64, c_void_p, c_void_p, c_void_p, c_void_p,
                                   c_void_p, POINTER(PcaInfo)]),
+    "sb2_tsvd_csr_f32": (c_int32, [c_void_p, c_int64, c_int32, c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_double,
+                                   c_uint64, c_void_p, c_void_p, c_void_p, c_void_p, POINTER(PcaInfo)]),
     "sb2_pca_stream_accumulate_f32": (c_int32, [c_void_p, c_int64, c_int32, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "sb2_pca_stream_solve_f32": (c_int32, [c_void_p, c_int64, c_int32, c_void_p, c_void_p, c_int32, c_int32, c_double,
                                            c_uint64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,

@@ -236,6 +236,25 @@ def pca_csr(x, n_comps: int, *, solver: int = 0, max_iter: int = 0, tol: float =
     return out
 
 
+def tsvd_csr(x, n_comps: int, *, solver: int = 1, seed: int = 0, ctx=None):
+    """Truncated SVD of a scipy CSR (no centring; `sc.pp.pca(zero_center=False)`): host arrays out, keys as `pca_csr`."""
+    torch = _torch()
+    ctx = ctx or _abi.default_context()
+    n, g = x.shape
+    d_indptr, d_indices, d_data = csr_to_device(x)
+    x_pca = torch.empty((n, n_comps), dtype=torch.float32, device="cuda")
+    comps = torch.empty((n_comps, g), dtype=torch.float32, device="cuda")
+    var = np.empty(n_comps, np.float64)
+    ratio = np.empty(n_comps, np.float64)
+    info = PcaInfo()
+    check(ctx.lib.sb2_tsvd_csr_f32(ctx.handle, n, g, ptr(d_indptr), ptr(d_indices), ptr(d_data), n_comps, solver, 0, 0.0, seed,
+                                   ptr(x_pca), ptr(comps), ptr(var), ptr(ratio), byref(info)))
+    h_x, h_c = _to_host(x_pca, comps)
+    RESIDENT.put(h_x, x_pca)
+    return dict(X_pca=h_x, components=h_c, variance=var, variance_ratio=ratio, iterations=info.iterations,
+                converged=bool(info.converged), max_rel_residual=info.max_rel_residual, total_var=info.total_var)
+
+
 def pca_csr_chunked(x, n_comps: int, *, chunk_size: int, seed: int = 0, ctx=None):
     """Out-of-core PCA of a host scipy CSR: the rows stream through the device `chunk_size` at a time (two passes: Gram
     accumulation, projection); device memory holds one chunk + the g x g Gram matrix.  Same outputs as `pca_csr`."""

@@ -940,7 +940,7 @@ static int32_t pca_core(sb2_ctx* ctx, int64_t n, int64_t n_total, int32_t g, con
                         const int32_t* d_indices, const float* d_data, int32_t k, int32_t solver, int32_t max_iter,
                         double tol, uint64_t seed, float* d_x_pca, float* d_components, double* h_var,
                         double* h_var_ratio, double* h_mean, sb2_pca_info* info, const double* pre_stats,
-                        const double* pre_gram, float* d_proj_out, float* d_shift_out, int32_t* l_out) {
+                        const double* pre_gram, float* d_proj_out, float* d_shift_out, int32_t* l_out, bool center = true) {
   const bool streamed = pre_stats != nullptr;
   SB2_CHECK_ARG(ctx && (streamed || (d_indptr && d_x_pca)) && d_components && h_var && h_var_ratio && h_mean, "null pointer");
   SB2_CHECK_ARG(!streamed || (pre_gram && d_proj_out && d_shift_out && l_out), "streamed PCA needs the Gram matrix and the projection outputs");
@@ -984,7 +984,12 @@ static int32_t pca_core(sb2_ctx* ctx, int64_t n, int64_t n_total, int32_t g, con
     total_var += (hs[g + j] - nt * mu * mu) / (nt - 1.0);  // per-gene variance, ddof=1 (_pca.py:727-729)
   }
   SB2_TRY(scr.alloc(&w.d_mu, (size_t)g));
-  SB2_CUDA(cudaMemcpyAsync(w.d_mu, h_mean, sizeof(double) * g, cudaMemcpyHostToDevice, st));
+  // zero_center=False (TruncatedSVD semantics): the operator is X^T X itself - the device copy of mu is all zeros, so neither
+  // the Gram centring nor the SpMM shift does anything; the true column means stay in h_mean for the variance formulas
+  double full_var0 = 0.0;   // sum of per-gene variances with ddof = 0 (TruncatedSVD.explained_variance_ratio_'s denominator)
+  for (int j = 0; j < g; ++j) full_var0 += hs[g + j] / nt - h_mean[j] * h_mean[j];
+  if (center) SB2_CUDA(cudaMemcpyAsync(w.d_mu, h_mean, sizeof(double) * g, cudaMemcpyHostToDevice, st));
+  else SB2_CUDA(cudaMemsetAsync(w.d_mu, 0, sizeof(double) * g, st));
 
   const int gl = (g < l) ? g : l;  // effective block width for tiny g handled below
   (void)gl;
@@ -1190,10 +1195,25 @@ static int32_t pca_core(sb2_ctx* ctx, int64_t n, int64_t n_total, int32_t g, con
       SB2_TRY(launch_spmm(ctx, n, l, d_indptr, d_indices, d_data, w.d_Bf, d_shift, d_x_pca, k, k));
     }
   }
-  for (int j = 0; j < k; ++j) {
-    const double ev = std::max(theta[j], 0.0) / (nt - 1.0);  // explained_variance_ = S^2/(n-1) (_pca.py:760-779)
-    h_var[j] = ev;
-    h_var_ratio[j] = total_var > 0.0 ? ev / total_var : 0.0;
+  if (center) {
+    for (int j = 0; j < k; ++j) {
+      const double ev = std::max(theta[j], 0.0) / (nt - 1.0);  // explained_variance_ = S^2/(n-1) (_pca.py:760-779)
+      h_var[j] = ev;
+      h_var_ratio[j] = total_var > 0.0 ? ev / total_var : 0.0;
+    }
+  } else {
+    // TruncatedSVD (sklearn/decomposition/_truncated_svd.py): explained_variance_ = np.var(X_transformed, axis=0) (ddof 0)
+    // = theta_j / n - (mean of column j)^2, the column mean of X V being mu . v_j; ratio against sum_g var_g (ddof 0)
+    std::vector<double> hV((size_t)gp * l);
+    SB2_CUDA(cudaMemcpyAsync(hV.data(), d_V, sizeof(double) * (size_t)gp * l, cudaMemcpyDeviceToHost, st));
+    SB2_CUDA(cudaStreamSynchronize(st));
+    for (int j = 0; j < k; ++j) {
+      double m = 0.0;
+      for (int r = 0; r < g; ++r) m += h_mean[r] * hV[(size_t)r * l + j];
+      const double ev = std::max(theta[j], 0.0) / nt - m * m;
+      h_var[j] = ev;
+      h_var_ratio[j] = full_var0 > 0.0 ? ev / full_var0 : 0.0;
+    }
   }
   SB2_CUDA(cudaStreamSynchronize(st));
   if (info) {
@@ -1211,6 +1231,18 @@ int32_t sb2_pca_csr_f32(sb2_ctx* ctx, int64_t n, int64_t n_total, int32_t g, con
                         double* h_var_ratio, double* h_mean, sb2_pca_info* info) {
   return pca_core(ctx, n, n_total, g, d_indptr, d_indices, d_data, k, solver, max_iter, tol, seed, d_x_pca, d_components, h_var,
                   h_var_ratio, h_mean, info, nullptr, nullptr, nullptr, nullptr, nullptr);
+}
+
+// sc.pp.pca(zero_center=False): sklearn TruncatedSVD (src/scanpy/preprocessing/_pca/__init__.py:309-336) - top-k singular
+// triplets of X itself; d_x_pca = X V = U Sigma, components sign-fixed like svd_flip(u_based_decision=False)
+int32_t sb2_tsvd_csr_f32(sb2_ctx* ctx, int64_t n, int32_t g, const int64_t* d_indptr, const int32_t* d_indices,
+                         const float* d_data, int32_t k, int32_t solver, int32_t max_iter, double tol, uint64_t seed,
+                         float* d_x_pca, float* d_components, double* h_var, double* h_var_ratio, sb2_pca_info* info) {
+  SB2_CHECK_ARG(ctx && ctx->n_ranks == 1, "sb2_tsvd_csr_f32 is single-rank");
+  SB2_CHECK_ARG(g >= 1, "g");
+  std::vector<double> mean((size_t)g);
+  return pca_core(ctx, n, n, g, d_indptr, d_indices, d_data, k, solver, max_iter, tol, seed, d_x_pca, d_components, h_var,
+                  h_var_ratio, mean.data(), info, nullptr, nullptr, nullptr, nullptr, nullptr, false);
 }
 
 // ---- out-of-core / chunked PCA (sc.pp.pca(chunked=True), src/scanpy/preprocessing/_pca/__init__.py:245-271) ----

@@ -70,8 +70,6 @@ def pca(data, n_comps: int | None = None, *, layer: str | None = None, obsm: str
     start = log_start("computing PCA")
     if (layer is not None or obsm is not None) and chunked:
         raise NotImplementedError("Cannot use `layer`/`obsm` and `chunked` at the same time.")
-    if not zero_center:
-        raise NotImplementedError("`zero_center=False` (TruncatedSVD) is not implemented in scanpy_b200.")
     return_anndata = is_anndata_like(data)
     if return_anndata:
         adata = data.copy() if copy else data
@@ -108,8 +106,17 @@ def pca(data, n_comps: int | None = None, *, layer: str | None = None, obsm: str
         raise ValueError(f"n_components={n_comps!r} must be between 1 and min(n_samples, n_features)="
                          f"{min(n_obs, n_vars)!r} with svd_solver='arpack'")
     xc = x if backed else as_csr_f32(x)
-    solver = _solver_code(svd_solver, n_vars=n_vars)
-    if chunked:
+    solver = _solver_code(svd_solver, n_vars=n_vars) if (zero_center and not chunked) else 1
+    if not zero_center and not chunked:
+        # sklearn TruncatedSVD (_pca/__init__.py:309-336); its solver names are 'arpack' | 'randomized' (default) - both are
+        # served by the exact device solver
+        if svd_solver not in (None, "arpack", "randomized", "b200_spmm"):
+            warn(f"Ignoring {svd_solver=} and using arpack, TruncatedSVD only supports ['arpack', 'randomized'].", UserWarning)
+        if backed:
+            raise NotImplementedError("`zero_center=False` on an on-disk matrix is not implemented in scanpy_b200.pp.pca")
+        out = _ops.tsvd_csr(xc, n_comps, solver=0 if (svd_solver == "b200_spmm" or n_vars > 8192) else 1, seed=seed_from_rng(rng))
+    elif chunked:
+        # (the reference ignores zero_center / svd_solver here too: "Ignoring zero_center, rng, svd_solver", :246-247)
         # the reference feeds row chunks to IncrementalPCA and expects the full PCA's result (tests/test_pca.py:357-386);
         # here the chunks stream through the exact Gram route (out-of-core: one chunk on the device at a time)
         out = _ops.pca_csr_chunked(xc, n_comps, chunk_size=settings.chunk_size if chunk_size is None else chunk_size,

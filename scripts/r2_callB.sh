@@ -1,8 +1,7 @@
 #!/bin/bash
-# 2-GPU sanity of the sharded path (gpurun --gpus 2): 2-GPU == 1-GPU results, then the bench line at N = 2
+# 2-GPU sanity of the sharded path (gpurun --gpus 2): the bench line at N = 2 with its parity block (labels_sha1 must equal the N = 1 run's)
 mkdir -p gpurun_out
-timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29512 scripts/dev_multi_gpu.py > gpurun_out/r2_multi_check.log 2>&1; tail -8 gpurun_out/r2_multi_check.log | cut -c1-300
-SB2_TIMING=1 timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 5 --warmup 3 > gpurun_out/r2_bench_n2.json 2> gpurun_out/r2_bench_n2.err
+SB2_TIMING=1 timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 5 --warmup 3 --no-cpu-baseline > gpurun_out/r2_bench_n2.json 2> gpurun_out/r2_bench_n2.err
 python - <<'P'
 import json
 d=json.loads(open('gpurun_out/r2_bench_n2.json').read().strip().splitlines()[-1])

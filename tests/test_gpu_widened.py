@@ -388,3 +388,30 @@ def test_pca_overlapped_upload_equals_plain_upload(monkeypatch):
     np.testing.assert_allclose(over["components"], plain["components"], atol=1e-6)
     np.testing.assert_allclose(over["variance"], plain["variance"], rtol=1e-10)
     np.testing.assert_allclose(over["mean"], plain["mean"], rtol=1e-12, atol=1e-15)
+
+
+@pytest.mark.parametrize("solver", [None, "b200_spmm"])
+def test_pca_zero_center_false_matches_truncated_svd(solver):
+    """`zero_center=False` = sklearn TruncatedSVD (src/scanpy/preprocessing/_pca/__init__.py:309-336): X V, V^T with
+    svd_flip signs, np.var-based explained variance; checked against the exact arpack solver in float64."""
+    from oracle import pca as opca
+
+    x, _ = synth_scipy(5000, 700, n_clusters=8, r=40)
+    k = 20
+    ref = opca.truncated_svd_arpack(x, k)
+    ad = sb.MiniAnnData(x)
+    sb.pp.pca(ad, n_comps=k, zero_center=False, svd_solver=solver)
+    xp = opca.align_signs(ad.obsm["X_pca"].astype(np.float64), ref["X_pca"])
+    rel = np.linalg.norm(xp - ref["X_pca"], axis=0) / np.linalg.norm(ref["X_pca"], axis=0)
+    tol = 1e-4 if solver is None else 2e-3   # the SpMM route runs float32 passes (its noise floor / the spectral gap)
+    assert rel.max() < tol, rel.max()
+    assert ad.uns["pca"]["params"]["zero_center"] is False
+    np.testing.assert_allclose(ad.uns["pca"]["variance"], ref["variance"], rtol=2e-4 if solver is None else 5e-3)
+    np.testing.assert_allclose(ad.uns["pca"]["variance_ratio"], ref["variance_ratio"], rtol=2e-4 if solver is None else 5e-3)
+    pcs = ad.varm["PCs"].T
+    np.testing.assert_allclose(np.abs(pcs), np.abs(ref["components"]), atol=2e-4 if solver is None else 5e-3)
+    # svd_flip(u_based_decision=False): the largest-|.| loading of every component is positive, as in the reference's output
+    assert (pcs[np.arange(k), np.abs(pcs).argmax(axis=1)] > 0).all()
+    # the first component is the mean direction: far from the centred PCA's
+    sb.pp.pca(ad, n_comps=k, key_added="centred")
+    assert abs(ad.obsm["centred"][:, 0].mean()) < 1e-3 < abs(ad.obsm["X_pca"][:, 0].mean())
