@@ -414,6 +414,15 @@ def run_b200(a, rank, world, local_rank):
                 stages=dict(pca_iterations=out["pca"]["iterations"], pca_converged=out["pca"]["converged"],
                             knn_uncertified_rows=ki["n_uncertified"], knn_resweep_rows=ki.get("n_resweep", 0), leiden=out["leiden_info"], n_communities=out["n_communities"],
                             modularity=out["modularity"]))
+    # per-stage device times of ONE extra, untimed step (CUDA events between the stages of pipeline_sharded on rank 0): where
+    # the step goes at this N - the replicated stages (connectivities, leiden, the dense part of pca) are the serial fraction
+    try:
+        evs = []
+        sbd.pipeline_sharded(ctx, *d_csr, bounds, rank, g, n_pcs=a.n_pcs, n_neighbors=a.k, solver=1, seed=0, stage_events=evs)
+        barrier()
+        line["stages"]["stage_ms"] = {name: round(evs[i - 1][1].elapsed_time(ev), 3) for i, (name, ev) in enumerate(evs) if i > 0}
+    except Exception as exc:  # never lose the bench line over a diagnostic
+        line["stages"]["stage_ms"] = {"error": repr(exc)[:200]}
     note("parity checks")
     if not a.no_parity:
         line["stages"]["parity"] = parity_checks(a, out, x_local if world == 1 else None, labels_local, (r0, r1))

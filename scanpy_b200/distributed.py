@@ -77,7 +77,7 @@ def attach_comm(ctx) -> None:
 
 def pipeline_sharded(ctx, d_indptr, d_indices, d_data, bounds, rank: int, g: int, *, n_pcs: int = 50,
                      n_neighbors: int = 15, solver: int = 1, resolution: float = 1.0, n_iterations: int = -1,
-                     seed: int = 0, ops=None):
+                     seed: int = 0, ops=None, stage_events=None):
     """pca -> neighbors -> leiden on this rank's CSR row shard; returns device tensors + stage info.
 
     `ops` defaults to the CUDA drivers in `_ops`; tests inject a stand-in to exercise the sharding
@@ -85,17 +85,33 @@ def pipeline_sharded(ctx, d_indptr, d_indices, d_data, bounds, rank: int, g: int
     """
     if ops is None:
         from . import _ops as ops
+    def mark(name):
+        # stage_events: a list the caller passes to get (name, CUDA event) marks between the stages (bench.py's stage_ms)
+        if stage_events is not None:
+            import torch
+
+            ev = torch.cuda.Event(enable_timing=True)
+            ev.record()
+            stage_events.append((name, ev))
+
     n_total = bounds[-1][1]
     r0, r1 = bounds[rank]
+    mark("start")
     pca = ops.pca_csr_device(ctx, d_indptr, d_indices, d_data, r1 - r0, g, n_pcs, solver=solver, seed=seed,
                              n_total=n_total)
+    mark("pca")
     x_all = allgather_rows(pca["X_pca"], bounds, rank) if len(bounds) > 1 else pca["X_pca"]
+    mark("allgather_x_pca")
     idx, dist, kinfo = ops.knn_device(ctx, x_all, n_neighbors, q0=r0, n_query=r1 - r0)
+    mark("knn")
     if len(bounds) > 1:
         idx = allgather_rows(idx, bounds, rank)
         dist = allgather_rows(dist, bounds, rank)
+    mark("allgather_knn")
     indptr, indices, data, _, _ = ops.fuzzy_simplicial_set_device(ctx, idx, dist, n_total, n_neighbors)
+    mark("connectivities")
     member, q, nc, linfo = ops.leiden_device(ctx, indptr, indices, data, n_total, resolution=resolution,
                                              n_iterations=n_iterations, seed=seed)
+    mark("leiden")
     return dict(X_pca_local=pca["X_pca"], X_pca=x_all, knn_idx=idx, knn_dist=dist, conn=(indptr, indices, data),
                 membership=member, modularity=q, n_communities=nc, pca=pca, knn_info=kinfo, leiden_info=linfo)
