@@ -14,7 +14,7 @@ import numpy as np
 import pandas as pd
 
 from . import _ops
-from ._compat import accepts_legacy_random_state, log_done, log_start, meta_random_state, seed_from_rng, warn
+from ._compat import LegacyRng, accepts_legacy_random_state, log_done, log_start, meta_random_state, seed_from_rng, warn
 
 
 def _validate_flavor(flavor, *, partition_type, directed) -> str:
@@ -154,7 +154,8 @@ def louvain(adata, resolution: float | None = None, *, random_state=0, restrict_
         adj = adj.copy()
         adj.data[:] = 1.0
     gamma = 1.0 if (resolution is None or flavor == "igraph") else float(resolution)
-    seed = 0 if random_state is None else int(random_state)
+    # `random_state` is the legacy form here (int | None | RandomState, _louvain.py:53): fold it to the kernels' integer seed
+    seed = int(random_state) if isinstance(random_state, (int, np.integer)) else seed_from_rng(LegacyRng(random_state))
     groups, _q, _info = _ops.louvain(adj, resolution=gamma, seed=seed)
     if restrict_to is not None:
         if key_added == "louvain":

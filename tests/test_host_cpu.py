@@ -257,3 +257,71 @@ def test_zarr_csr_reader_on_the_reference_fixture():
     assert (mg.read_zarr_array(zz, "layers/counts/indptr") == m.indptr).all()
     with pytest.raises(NotImplementedError, match="csr_matrix"):
         ZarrCSR(fixture, "obsm")
+
+
+# ------------------------------------------------------------------------------------------ widened tools: host contracts
+def test_widened_tools_argument_contracts_without_gpu():
+    """Everything the widened entry points decide BEFORE they touch the device (reference error texts / rules):
+    tl.umap (_umap.py:150-158,217-219), tl.diffmap (_diffmap.py:94-99), tl.paga (_paga.py:108-124), tl.louvain
+    (_louvain.py:129-131,177-179), metrics.modularity (_metrics.py:158-176), pp.scale's mask rules (get/get.py:633-651)."""
+    x = sparse.random(40, 12, density=0.3, format="csr", dtype=np.float32, random_state=0)
+    ad = MiniAnnData(x)
+    with pytest.raises(ValueError, match=r"Did not find .uns\['neighbors'\]. Run `sc.pp.neighbors` first."):
+        tl.umap(ad)
+    with pytest.raises(ValueError, match="You need to run `pp.neighbors` first"):
+        tl.diffmap(ad)
+    with pytest.raises(ValueError, match="You need to run `pp.neighbors` first"):
+        tl.paga(ad)
+    with pytest.raises(ValueError, match="You need to run `pp.neighbors` first"):
+        tl.louvain(ad)
+    # a neighbours entry is enough to get past the first gate
+    g = sparse.random(40, 40, density=0.2, format="csr", dtype=np.float32, random_state=1)
+    g = (g + g.T).tocsr()
+    ad.obsp["connectivities"], ad.obsp["distances"] = g, g.astype(np.float64)
+    ad.uns["neighbors"] = dict(connectivities_key="connectivities", distances_key="distances", params=dict(method="umap"))
+    with pytest.raises(ValueError, match="Unknown method"):
+        tl.umap(ad, method="tsne")
+    with pytest.raises(NotImplementedError, match="paga"):
+        tl.umap(ad, init_pos="paga")
+    with pytest.raises(ValueError, match="init_pos must have shape"):
+        tl.umap(ad, init_pos=np.zeros((40, 3), np.float32))
+    with pytest.raises(ValueError, match="greater than 2"):
+        tl.diffmap(ad, n_comps=2)
+    with pytest.raises(ValueError, match="tl.leiden` or `tl.louvain"):
+        tl.paga(ad)
+    with pytest.raises(KeyError, match="not found"):
+        tl.paga(ad, groups="nope")
+    ad.obs["grp"] = pd.Categorical(["a", "b"] * 20)
+    with pytest.raises(NotImplementedError, match="v1.0"):
+        tl.paga(ad, groups="grp", model="v1.0")
+    with pytest.raises(ValueError, match="needs to be one of"):
+        tl.paga(ad, groups="grp", model="v9")
+    with pytest.raises(ValueError, match='`flavor` needs to be "vtraag" or "igraph" or "taynaud"'):
+        tl.louvain(ad, flavor="nope")
+    with pytest.raises(ValueError, match="only a valid argument when `flavour` is \"vtraag\""):
+        tl.louvain(ad, flavor="igraph", partition_type=object)
+    with pytest.raises(TypeError, match="`labels` must be provided as array"):
+        sb.metrics.modularity(g, "leiden", is_directed=False)
+    with pytest.raises(TypeError, match="`is_directed` must be provided"):
+        sb.metrics.modularity(g, np.zeros(40, int))
+    with pytest.raises(ValueError, match="undirected"):
+        sb.metrics.modularity(ad, is_directed=True)
+    ad.uns["leiden"] = dict(modularity=0.25)
+    assert sb.metrics.modularity(ad, mode="retrieve") == 0.25
+    with pytest.raises(ValueError, match="must be a string"):
+        sb.metrics.modularity(ad, np.zeros(40, int), mode="update")
+    with pytest.raises(ValueError, match="Cannot use refererence for mask without providing anndata"):
+        pp.scale(x, mask_obs="cells")
+    with pytest.raises(ValueError, match="Mask array must be boolean"):
+        pp.scale(x, mask_obs=np.ones(40, int))
+    with pytest.raises(ValueError, match="shape of the mask"):
+        pp.scale(x, mask_obs=np.ones(7, bool))
+    with pytest.raises(NotImplementedError, match="layer"):
+        pp.scale(ad, layer="counts")
+    # find_ab_params: umap-learn's published defaults for (spread 1.0, min_dist 0.5) and (1.0, 0.1)
+    from scanpy_b200._graph_tools import find_ab_params
+
+    a, b = find_ab_params(1.0, 0.5)
+    assert a == pytest.approx(0.5830300, rel=1e-5) and b == pytest.approx(1.3341669, rel=1e-5)
+    a, b = find_ab_params(1.0, 0.1)
+    assert a == pytest.approx(1.5769, rel=1e-3) and b == pytest.approx(0.8951, rel=1e-3)
