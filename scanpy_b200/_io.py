@@ -135,7 +135,13 @@ class _Array1D:
                 return np.full(self.inner, self.fill, self.dtype)
         if self.zstd:
             buf = _zstd_decompress(buf, nbytes)
-        return np.frombuffer(buf, self.dtype, count=self.inner)
+        have = len(buf) // self.dtype.itemsize
+        if have >= self.inner:
+            return np.frombuffer(buf, self.dtype, count=self.inner)
+        # a writer may store the last chunk of an array unpadded: fill the tail
+        out = np.full(self.inner, self.fill, self.dtype)
+        out[:have] = np.frombuffer(buf, self.dtype, count=have)
+        return out
 
     def read(self, lo: int, hi: int) -> np.ndarray:
         """Elements [lo, hi): only the inner chunks overlapping the range are decoded."""
