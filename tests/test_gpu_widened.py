@@ -415,3 +415,25 @@ def test_pca_zero_center_false_matches_truncated_svd(solver):
     # the first component is the mean direction: far from the centred PCA's
     sb.pp.pca(ad, n_comps=k, key_added="centred")
     assert abs(ad.obsm["centred"][:, 0].mean()) < 1e-3 < abs(ad.obsm["X_pca"][:, 0].mean())
+
+
+def test_clustering_reproduces_the_reference_fixtures_stored_louvain(pbmc68k_graph):
+    """The reference's own label-level golden (see tests/test_oracle_leiden_guarantees.py): `obs/louvain` of the in-tree
+    pbmc68k_reduced fixture = scanpy's `sc.tl.louvain` defaults on the stored connectivities.  `sb.tl.louvain` with the same
+    defaults (vtraag, unweighted), and `sb.tl.leiden(use_weights=False)`, must land on that partition as closely as
+    independent CPU optimisers do (networkx Louvain 0.94-0.97, sequential oracle 0.94-0.98)."""
+    f = pbmc68k_graph
+    n = len(f["conn_indptr"]) - 1
+    conn = sparse.csr_matrix((f["conn_data"].astype(np.float32), f["conn_indices"], f["conn_indptr"]), shape=(n, n))
+    stored = f["louvain_codes"].astype(int)
+    ad = sb.MiniAnnData(sparse.csr_matrix((n, 3), dtype=np.float32))
+    ad.obsp["connectivities"] = conn
+    ad.uns["neighbors"] = dict(connectivities_key="connectivities", distances_key="distances", params=dict(method="umap"))
+    sb.tl.louvain(ad)
+    lv = ad.obs["louvain"].to_numpy().astype(int)
+    sb.tl.leiden(ad, use_weights=False, flavor="igraph")
+    ld = ad.obs["leiden"].to_numpy().astype(int)
+    a_lv, a_ld = adjusted_rand_score(stored, lv), adjusted_rand_score(stored, ld)
+    print(f"\n[pbmc68k stored louvain] ARI device louvain {a_lv:.3f} ({lv.max() + 1} clusters), device leiden {a_ld:.3f} ({ld.max() + 1})")
+    assert a_lv > 0.9 and a_ld > 0.9, (a_lv, a_ld)
+    assert 10 <= lv.max() + 1 <= 12 and 10 <= ld.max() + 1 <= 12
