@@ -22,7 +22,10 @@ What each module is, and how it is pinned to the reference (scverse/scanpy @ fab
 * `oracle.leiden`   - C restatement (oracle/leiden_ref.c) of the Leiden algorithm as run by
                       leidenalg.find_partition(RBConfigurationVertexPartition) (leidenalg >= 0.10.1,
                       NOT vendored, not installed; call site src/scanpy/tools/_leiden.py:184-187).
-                      PARITY UNPINNED at label level: the reference's tests hold no Leiden label
-                      golden (tests/test_clustering.py pins properties only), so this restatement is
-                      checked against those properties + planted partitions + networkx modularity.
+                      Label level: the reference's tests hold no Leiden label golden
+                      (tests/test_clustering.py pins properties only); the restatement is checked against
+                      those properties, Traag et al.'s guarantees, planted partitions, networkx modularity,
+                      and the one clustering the reference itself wrote to disk - the in-tree fixture's
+                      `obs/louvain` (sc.tl.louvain defaults), reproduced at ARI 0.94-0.98 on the unweighted
+                      graph (tests/test_oracle_leiden_guarantees.py).
 """
