@@ -123,6 +123,7 @@ def main() -> None:
         "conn_indices": read_zarr_array(z, "obsp/connectivities/indices"),
         "conn_indptr": read_zarr_array(z, "obsp/connectivities/indptr"),
         "louvain_codes": read_zarr_array(z, "obs/louvain/codes"),
+        "X_umap": read_zarr_array(z, "obsm/X_umap"),   # the reference's own sc.tl.umap output on this graph
         "n_neighbors": read_zarr_array(z, "uns/neighbors/params/n_neighbors"),
     }
     np.savez_compressed(OUT / "pbmc68k_reduced_graph.npz", **fx)

@@ -437,3 +437,31 @@ def test_clustering_reproduces_the_reference_fixtures_stored_louvain(pbmc68k_gra
     print(f"\n[pbmc68k stored louvain] ARI device louvain {a_lv:.3f} ({lv.max() + 1} clusters), device leiden {a_ld:.3f} ({ld.max() + 1})")
     assert a_lv > 0.9 and a_ld > 0.9, (a_lv, a_ld)
     assert 10 <= lv.max() + 1 <= 12 and 10 <= ld.max() + 1 <= 12
+
+
+def test_umap_quality_matches_the_reference_fixtures_stored_embedding(pbmc68k_graph):
+    """Device `tl.umap` on the fixture's stored connectivities vs the embedding the reference itself stored there
+    (`obsm/X_umap`; see tests/test_oracle_goldens.py for what can and cannot be compared)."""
+    from sklearn.manifold import trustworthiness
+    from sklearn.metrics import silhouette_score
+    from sklearn.neighbors import NearestNeighbors
+
+    f = pbmc68k_graph
+    n = 700
+    conn = sparse.csr_matrix((f["conn_data"].astype(np.float32), f["conn_indices"], f["conn_indptr"]), shape=(n, n))
+    stored, lab, x30 = f["X_umap"], f["louvain_codes"].astype(int), f["X_pca"][:, :30]
+    ad = sb.MiniAnnData(sparse.csr_matrix((n, 3), dtype=np.float32))
+    ad.obsp["connectivities"] = conn
+    ad.uns["neighbors"] = dict(connectivities_key="connectivities", distances_key="distances", params=dict(method="umap"))
+    sb.tl.umap(ad)
+    emb = ad.obsm["X_umap"]
+
+    def nbrs(a, k=15):
+        return NearestNeighbors(n_neighbors=k + 1).fit(a).kneighbors(a, return_distance=False)[:, 1:]
+
+    ov = float(np.mean([len(set(p) & set(q)) / 15 for p, q in zip(nbrs(emb), nbrs(stored))]))
+    t_got, t_ref = trustworthiness(x30, emb, n_neighbors=10), trustworthiness(x30, stored, n_neighbors=10)
+    s_got, s_ref = silhouette_score(emb, lab), silhouette_score(stored, lab)
+    print(f"\n[pbmc68k stored X_umap] trustworthiness {t_got:.4f} (stored {t_ref:.4f}), silhouette {s_got:.3f} ({s_ref:.3f}), "
+          f"15-NN overlap with the stored embedding {ov:.3f} (sequential oracle: 0.64-0.65, oracle seed-vs-seed 0.675)")
+    assert t_got > t_ref - 0.015 and s_got > s_ref - 0.08 and ov > 0.55

@@ -215,3 +215,34 @@ def test_graph_tool_oracles_on_the_reference_fixture(pbmc68k_graph):
     assert tree.nnz == G - ncomp
     emb = og.simplicial_set_embedding(conn.astype(np.float32), n_epochs=200)
     assert np.isfinite(emb).all() and silhouette_score(emb, codes) > 0.1
+
+
+def test_umap_oracle_matches_the_reference_fixtures_stored_embedding(pbmc68k_graph):
+    """A reference-WRITTEN UMAP result: the in-tree fixture stores `obsm/X_umap`, scanpy's own `sc.tl.umap` output on the
+    stored connectivities.  Coordinates cannot be compared (different seed / library version), quality can: the sequential
+    restatement must preserve the X_pca[:, :30] neighbourhoods (the space the stored graph was built in)
+    as well as the stored embedding does, separate the stored clusters as well, and agree with the stored embedding's
+    15-neighbourhoods about as much as two of its own seeds agree with each other."""
+    from sklearn.manifold import trustworthiness
+    from sklearn.metrics import silhouette_score
+    from sklearn.neighbors import NearestNeighbors
+
+    from oracle import graph_tools as og
+
+    f = pbmc68k_graph
+    n = 700
+    conn = sparse.csr_matrix((f["conn_data"].astype(np.float32), f["conn_indices"], f["conn_indptr"]), shape=(n, n))
+    stored, lab, x30 = f["X_umap"], f["louvain_codes"].astype(int), f["X_pca"][:, :30]
+
+    def nbrs(a, k=15):
+        return NearestNeighbors(n_neighbors=k + 1).fit(a).kneighbors(a, return_distance=False)[:, 1:]
+
+    def overlap(a, b):
+        return float(np.mean([len(set(p) & set(q)) / 15 for p, q in zip(nbrs(a), nbrs(b))]))
+
+    t_ref, s_ref = trustworthiness(x30, stored, n_neighbors=10), silhouette_score(stored, lab)
+    e0, e1 = og.simplicial_set_embedding(conn, seed=0), og.simplicial_set_embedding(conn, seed=5)
+    for e in (e0, e1):
+        assert abs(trustworthiness(x30, e, n_neighbors=10) - t_ref) < 0.01      # measured: 0.9513-0.9526 vs 0.9512
+        assert abs(silhouette_score(e, lab) - s_ref) < 0.06                      # 0.49-0.51 vs 0.506
+    assert overlap(e0, stored) > overlap(e0, e1) - 0.08                           # 0.65 vs 0.675
